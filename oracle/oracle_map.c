@@ -1,0 +1,243 @@
+/* oracle_map.c -- per-read driver restated on the CPU (test oracle; see oracle.h).
+ *
+ * Follows reference src/sigfish.c:
+ *   normalise_single 424-505, init_aln 507-520, update_aln 575-626,
+ *   paf_str 628-660, aln_to_str 796-826, dtw_single 828-985.
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle.h"
+
+#define KEEP 5 /* SECONDARY_CAP, sigfish.h:41 */
+
+typedef struct {
+    float score;
+    int32_t rid;
+    int32_t pos_st;
+    int32_t pos_end;
+    char strand;
+} cand_t;
+
+/* sigfish.c:424-505.  Window selection, then z-score of the event means inside it. */
+int orc_window_normalise(orc_event_t *ev, int64_t *n_events, uint32_t flags, int32_t q, int32_t p,
+                         int64_t *qstart, int64_t *qend, int32_t *status)
+{
+    int64_t n = *n_events;
+    *status = 0;
+    *qstart = 0;
+    *qend = 0;
+    if (n <= 0)
+        return 0;
+    int64_t lo, hi;
+    if (!(flags & ORC_END)) { /* sigfish.c:435-462 (auto query start, p < 0, is not restated here) */
+        lo = p;
+        hi = lo + q;
+        if (lo + 25 > n) {
+            lo = hi = 0;
+            n = 0;
+            *status |= 1;
+        } else if (hi > n) {
+            hi = n;
+            *status |= 2;
+        }
+    } else { /* sigfish.c:464-478 */
+        lo = n - p - q;
+        hi = n - p;
+        if (lo < 0) {
+            lo = 0;
+            *status |= 2;
+        }
+        if (hi < 0) {
+            hi = 0;
+            n = 0;
+            *status |= 1;
+        }
+    }
+    *qstart = lo;
+    *qend = hi;
+    *n_events = n;
+
+    /* sigfish.c:483-502 -- runs even for an ignored read (empty window) */
+    const float cnt = (float)(hi - lo);
+    float mean = 0.0f;
+    for (int64_t j = lo; j < hi; j++)
+        mean += ev[j].mean;
+    mean /= cnt;
+    float var = 0.0f;
+    for (int64_t j = lo; j < hi; j++) {
+        float d = ev[j].mean - mean;
+        var += d * d;
+    }
+    var /= cnt;
+    const float sd = (float)sqrt((double)var);
+    for (int64_t j = lo; j < hi; j++)
+        ev[j].mean = (ev[j].mean - mean) / sd;
+    return n > 0;
+}
+
+/* sigfish.c:575-626.  `list` is ordered worst (index 0) to best (index KEEP-1).  A new score
+ * is placed above every entry whose score is >= it, so of two equal scores the later one ranks
+ * better; entry 0 falls off. */
+static void keep_best(cand_t *list, float score, int32_t rid, int32_t pos, char strand,
+                      const float *cost, int qlen, int rlen)
+{
+    int slot = 0;
+    while (slot < KEEP && !(score > list[slot].score))
+        slot++;
+    if (slot == 0)
+        return;
+    for (int s = 0; s + 1 < slot; s++)
+        list[s] = list[s + 1];
+    cand_t *c = &list[slot - 1];
+    c->score = score;
+    c->rid = rid;
+    c->pos_end = pos;
+    c->strand = strand;
+    c->pos_st = -1;
+    if (pos < rlen) /* cdtw.c:107-108: path() refuses an out-of-range start column */
+        c->pos_st = orc_path_start(cost, qlen, rlen, pos < 0 ? rlen - 1 : pos);
+}
+
+/* sigfish.c:891-901 / 938-948 -- cut the last row into blocks of qlen columns; each block
+ * offers its first (strict <) minimum */
+static void offer_blocks(cand_t *list, const float *cost, int qlen, int rlen, int32_t rid, char strand)
+{
+    const float *last = cost + (size_t)(qlen - 1) * rlen;
+    for (int b = 0; b < rlen; b += qlen) {
+        float best = INFINITY;
+        int32_t at = -1;
+        for (int c = b; c < b + qlen && c < rlen; c++) {
+            if (last[c] < best) {
+                best = last[c];
+                at = c;
+            }
+        }
+        /* with no finite cell the reference passes min_pos = -1, i.e. pos = -1 - (qlen-1)*rlen */
+        int32_t pos = at >= 0 ? at : (int32_t)(-1 - (int64_t)(qlen - 1) * rlen);
+        keep_best(list, best, rid, pos, strand, cost, qlen, rlen);
+    }
+}
+
+/* sigfish.c:979: (int)round(...) of a double; x86-64 cvttsd2si yields INT_MIN when out of range */
+static int32_t to_int_x86(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        return INT_MIN;
+    return (int32_t)v;
+}
+
+/* sigfish.c:828-985 */
+void orc_align(const orc_ref_t *ref, const orc_event_t *ev, int64_t qstart, int64_t qend,
+               uint32_t flags, orc_hit_t *hit)
+{
+    const int rna = (flags & ORC_RNA) != 0;
+    const int qlen = (int)(qend - qstart);
+
+    cand_t list[KEEP];
+    for (int s = 0; s < KEEP; s++) {
+        list[s].score = INFINITY;
+        list[s].rid = -1;
+        list[s].pos_st = list[s].pos_end = -1;
+        list[s].strand = 0;
+    }
+
+    float *query = (float *)malloc(sizeof(float) * (size_t)(qlen > 0 ? qlen : 1));
+    for (int j = 0; j < qlen; j++) { /* 857-867: RNA reads are 3'->5', flip unless --invert */
+        if (rna && !(flags & ORC_INV))
+            query[qlen - 1 - j] = ev[qstart + j].mean;
+        else
+            query[j] = ev[qstart + j].mean;
+    }
+
+    for (int32_t r = 0; r < ref->num_ref; r++) {
+        const int rlen = ref->ref_lengths[r];
+        float *cost = (float *)malloc(sizeof(float) * (size_t)qlen * (size_t)rlen);
+        if (!(flags & ORC_DTW)) {
+            orc_subsequence(query, ref->forward[r], qlen, rlen, cost);
+            offer_blocks(list, cost, qlen, rlen, r, '+');
+        } else { /* 914-917: only the bottom-right cell competes */
+            float s = orc_std_dtw(query, ref->forward[r], qlen, rlen, cost);
+            keep_best(list, s, r, rlen - 1, '+', cost, qlen, rlen);
+        }
+        if (!rna) {
+            orc_subsequence(query, ref->reverse[r], qlen, rlen, cost);
+            offer_blocks(list, cost, qlen, rlen, r, '-');
+        }
+        free(cost);
+    }
+    free(query);
+
+    /* 969-983 */
+    const cand_t *w = &list[KEEP - 1];
+    hit->score = w->score;
+    hit->score2 = list[KEEP - 2].score;
+    hit->rid = w->rid;
+    hit->strand = w->strand;
+    hit->raw_pos_st = w->pos_st;
+    hit->raw_pos_end = w->pos_end;
+    if (w->rid >= 0) {
+        const int32_t rl = ref->ref_lengths[w->rid];
+        hit->pos_st = w->strand == '+' ? w->pos_st : rl - w->pos_end;
+        hit->pos_end = w->strand == '+' ? w->pos_end : rl - w->pos_st;
+        hit->pos_st += ref->ref_st_offset[w->rid];
+        hit->pos_end += ref->ref_st_offset[w->rid];
+    } else {
+        hit->pos_st = hit->pos_end = -1;
+    }
+    float ratio = 500 * (hit->score2 - hit->score) / hit->score;
+    int32_t mq = to_int_x86(round((double)ratio));
+    if (mq > 60)
+        mq = 60;
+    hit->mapq = (int32_t)(uint8_t)mq; /* aln_t.mapq is uint8_t (sigfish.h:153) */
+}
+
+void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,
+                  float offset, float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit)
+{
+    memset(hit, 0, sizeof(*hit));
+    hit->rid = -1;
+    if (n <= 0)
+        return;
+    orc_event_t *ev = NULL;
+    int64_t nev = orc_detect_events(raw, n, digitisation, offset, range, (flags & ORC_RNA) != 0, &ev);
+    hit->n_events = nev;
+    if (nev <= 0) {
+        free(ev);
+        return;
+    }
+    int64_t lo, hi;
+    int32_t st;
+    int64_t nkeep = nev;
+    int go = orc_window_normalise(ev, &nkeep, flags, q, p, &lo, &hi, &st);
+    hit->status = st;
+    hit->qstart = lo;
+    hit->qend = hi;
+    if (go) {
+        hit->mapped = 1;
+        /* sigfish.c:800-807 */
+        hit->start_raw = ev[lo].start;
+        /* uint64 + float is evaluated in fp32 and converted back (C usual arithmetic conversions) */
+        hit->end_raw = (uint64_t)((float)ev[hi - 1].start + ev[hi - 1].length);
+        orc_align(ref, ev, lo, hi, flags, hit);
+    }
+    free(ev);
+}
+
+/* sigfish.c:628-660 with the arguments aln_to_str passes (796-826) */
+int orc_paf_line(char *buf, size_t cap, const orc_hit_t *hit, const char *read_id,
+                 const char *rname, int32_t ref_seq_len, int64_t len_raw_signal)
+{
+    const uint64_t query_size = (uint64_t)(hit->qend - 1) - (uint64_t)hit->qstart;
+    const float block = (float)(hit->pos_end - hit->pos_st);
+    const float residue = block - hit->score * block / (float)query_size;
+    return snprintf(buf, cap,
+                    "%s\t%ld\t%ld\t%ld\t%c\t%s\t%d\t%d\t%d\t%d\t%d\t%d\ttp:A:P\td1:f:%.2f\td2:f:%.2f\n",
+                    read_id, (long)len_raw_signal, (long)hit->start_raw, (long)hit->end_raw,
+                    hit->strand, rname, ref_seq_len, hit->pos_st, hit->pos_end,
+                    to_int_x86(round((double)residue)), to_int_x86(round((double)block)),
+                    hit->mapq, (double)hit->score, (double)hit->score2);
+}

@@ -1,0 +1,157 @@
+"""Deterministic synthetic inputs for the `dtw` path.
+
+The real ONT pore-model tables (reference src/model.h) are absent from the
+reference mount, so every run -- reference binary, oracle and GPU path -- is
+driven by a seeded synthetic k-mer model written in the `--kmer-model` text
+format (reference src/model.c:60-109: optional `#k\\t<K>` line, header line,
+then 4^K positional rows `kmer\\tlevel_mean\\tlevel_stdv...`).
+
+All model values are multiples of 1/64 so that the `%.6f` text form parses back
+to exactly the same fp32 value on every path (no decimal->binary double rounding).
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+_BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+DNA_SCALING = dict(digitisation=8192.0, range=1402.882, offset=10.0, sampling_rate=4000.0)
+RNA_SCALING = dict(digitisation=2048.0, range=548.788, offset=-240.0, sampling_rate=3000.0)
+
+
+def make_model(k: int, seed: int = 7):
+    """level_mean in [60,130], level_stdv in [1,3], both on a 1/64 grid."""
+    rng = np.random.default_rng(seed * 1000003 + k)
+    n = 4 ** k
+    mean = (60.0 + rng.integers(0, 70 * 64, size=n) / 64.0).astype(np.float32)
+    stdv = (1.0 + rng.integers(0, 2 * 64, size=n) / 64.0).astype(np.float32)
+    return mean, stdv
+
+
+def write_model_file(path: str, k: int, mean: np.ndarray, stdv: np.ndarray) -> None:
+    n = 4 ** k
+    assert mean.shape[0] == n
+    idx = np.arange(n)
+    # k-mer text is ignored by the reader (rows are positional) but keep it right
+    cols = [(idx >> (2 * (k - 1 - i))) & 3 for i in range(k)]
+    kmers = _BASES[np.stack(cols, axis=1)].view(f"S{k}").ravel()
+    with open(path, "w") as f:
+        f.write(f"#k\t{k}\n")
+        f.write("kmer\tlevel_mean\tlevel_stdv\tsd_mean\tsd_stdv\n")
+        lines = [f"{kmers[i].decode()}\t{mean[i]:.6f}\t{stdv[i]:.6f}\t0.000000\t0.000000\n" for i in range(n)]
+        f.write("".join(lines))
+
+
+def random_sequence(n: int, rng: np.random.Generator) -> bytes:
+    return _BASES[rng.integers(0, 4, size=n)].tobytes()
+
+
+def write_fasta(path: str, names, seqs, width: int = 80) -> None:
+    with open(path, "w") as f:
+        for name, s in zip(names, seqs):
+            if isinstance(s, bytes):
+                s = s.decode()
+            f.write(f">{name}\n")
+            for i in range(0, len(s), width):
+                f.write(s[i:i + width] + "\n")
+
+
+def kmer_ranks(seq: bytes, k: int) -> np.ndarray:
+    """rank of every k-mer of seq (A,C,G,T -> 0..3, anything else -> 0), cf. ref.h:13-41"""
+    lut = np.zeros(256, dtype=np.int64)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"a", 0), (b"c", 1), (b"g", 2), (b"t", 3)):
+        lut[ch[0]] = v
+    b = lut[np.frombuffer(seq, dtype=np.uint8)]
+    n = len(seq) + 1 - k
+    r = np.zeros(n, dtype=np.int64)
+    for i in range(k):
+        r = (r << 2) | b[i:i + n]
+    return r
+
+
+def revcomp(seq: bytes) -> bytes:
+    tbl = bytearray(b"T" * 256)  # ref.h:62-65: anything unknown -> 'T'
+    for a, b in ((b"A", b"T"), (b"C", b"G"), (b"G", b"C"), (b"T", b"A"), (b"a", b"T"), (b"c", b"G"), (b"g", b"C"), (b"t", b"A")):
+        tbl[a[0]] = b[0]
+    return seq.translate(bytes(tbl))[::-1]
+
+
+def simulate_read(levels: np.ndarray, rng: np.random.Generator, scaling: dict,
+                  noise_pa: float = 1.5, mean_extra_dwell: float = 8.0, min_dwell: int = 2) -> np.ndarray:
+    """Squiggle for a sequence of k-mer levels: dwell = min_dwell + Geom, N(0,noise) pA noise,
+    quantised to int16 ADC counts with the given scaling (pa = (raw + offset) * range / digitisation)."""
+    dwell = min_dwell + rng.geometric(1.0 / (mean_extra_dwell + 1.0), size=levels.shape[0]) - 1
+    pa = np.repeat(levels.astype(np.float64), dwell)
+    pa = pa + rng.normal(0.0, noise_pa, size=pa.shape[0])
+    raw = np.rint(pa * scaling["digitisation"] / scaling["range"] - scaling["offset"])
+    return np.clip(raw, -32768, 32767).astype(np.int16)
+
+
+def simulate_reads(seqs, k: int, level_mean: np.ndarray, n_reads: int, seed: int, rna: bool = False,
+                   bases_per_read: int = 450, both_strands: bool = True, scaling: dict | None = None,
+                   adaptor_events: int = 0, min_samples: int = 0):
+    """Draw n_reads loci from the given sequences and simulate their raw signal.
+
+    DNA: a locus on either strand, read 5'->3' of that strand.
+    RNA: the 3' end of a transcript, sequenced 3'->5' (so k-mer levels are emitted in reverse).
+    Returns (list of int16 arrays, list of (contig index, strand, start) truth tuples)."""
+    rng = np.random.default_rng(seed)
+    scaling = scaling or (RNA_SCALING if rna else DNA_SCALING)
+    fwd_ranks = [kmer_ranks(s, k) for s in seqs]
+    rev_ranks = None if rna else [kmer_ranks(revcomp(s), k) for s in seqs]
+    sigs, truth = [], []
+    for _ in range(n_reads):
+        ci = int(rng.integers(0, len(seqs)))
+        n_k = fwd_ranks[ci].shape[0]
+        span = min(bases_per_read, n_k)
+        if rna:
+            st = n_k - span
+            lv = level_mean[fwd_ranks[ci][st:st + span]][::-1]
+            strand = "+"
+        else:
+            st = int(rng.integers(0, n_k - span + 1))
+            if both_strands and rng.integers(0, 2):
+                lv = level_mean[rev_ranks[ci][st:st + span]]
+                strand = "-"
+            else:
+                lv = level_mean[fwd_ranks[ci][st:st + span]]
+                strand = "+"
+        if adaptor_events:
+            lv = np.concatenate([rng.uniform(70, 110, size=adaptor_events).astype(np.float32), lv])
+        min_dwell = 6 if rna else 2
+        if min_samples:  # the reference's (dead) MAD trim has UB on reads shorter than ~500 samples
+            min_dwell = max(min_dwell, -(-min_samples // max(1, lv.shape[0])))
+        sigs.append(simulate_read(lv, rng, scaling, mean_extra_dwell=(18.0 if rna else 8.0), min_dwell=min_dwell))
+        truth.append((ci, strand, st))
+    return sigs, truth
+
+
+def write_slow5_ascii(path: str, read_ids, signals, rna: bool = False, kit: str | None = None,
+                      scaling: dict | None = None, scalings=None) -> None:
+    """ASCII SLOW5 v0.2.0 that the reference's slow5_open accepts."""
+    scaling = scaling or (RNA_SCALING if rna else DNA_SCALING)
+    kit = kit or ("sqk-rna002" if rna else "sqk-lsk109")
+    with open(path, "w") as f:
+        f.write("#slow5_version\t0.2.0\n#num_read_groups\t1\n")
+        f.write(f"@experiment_type\t{'rna' if rna else 'genomic_dna'}\n")
+        f.write(f"@sequencing_kit\t{kit}\n")
+        f.write("#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n")
+        f.write("#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n")
+        for i, (rid, sig) in enumerate(zip(read_ids, signals)):
+            sc = scalings[i] if scalings is not None else scaling
+            f.write(f"{rid}\t0\t{_g(sc['digitisation'])}\t{_g(sc['offset'])}\t{_g(sc['range'])}\t"
+                    f"{_g(sc['sampling_rate'])}\t{len(sig)}\t")
+            f.write(",".join(map(str, sig.tolist())))
+            f.write("\n")
+
+
+def _g(x: float) -> str:
+    # shortest decimal that round-trips the double (slow5 parses with strtod)
+    return repr(float(x))
+
+
+def tmpdir() -> str:
+    d = os.environ.get("SIGFISH_B200_TMP", "/tmp/sigfish_b200")
+    os.makedirs(d, exist_ok=True)
+    return d
