@@ -70,6 +70,9 @@ typedef struct {
 orc_ref_t *orc_ref_build(int32_t num_ref, const char *const *seqs, const int32_t *seq_lens,
                          const float *level_mean, int32_t kmer_size, uint32_t flags,
                          int32_t query_size);
+/* test helper: reference made of caller-given event arrays (flat, contig after contig) */
+orc_ref_t *orc_ref_from_events(int32_t num_ref, int32_t has_reverse, const int32_t *lens,
+                               const float *fwd_flat, const float *rev_flat);
 void orc_ref_free(orc_ref_t *r);
 /* accessors for ctypes */
 int32_t orc_ref_len(const orc_ref_t *r, int32_t i);
@@ -109,6 +112,9 @@ int orc_window_normalise(orc_event_t *ev, int64_t *n_events, uint32_t flags, int
 /* dtw_single (sigfish.c:828-985) on an already normalised event table */
 void orc_align(const orc_ref_t *ref, const orc_event_t *ev, int64_t qstart, int64_t qend,
                uint32_t flags, orc_hit_t *hit);
+
+/* test helper: orc_align on a bare array of normalised event means */
+void orc_align_means(const orc_ref_t *ref, const float *means, int32_t n, uint32_t flags, orc_hit_t *hit);
 
 /* event_single + normalise_single + dtw_single for one read */
 void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,

@@ -241,3 +241,18 @@ int orc_paf_line(char *buf, size_t cap, const orc_hit_t *hit, const char *read_i
                     to_int_x86(round((double)residue)), to_int_x86(round((double)block)),
                     hit->mapq, (double)hit->score, (double)hit->score2);
 }
+
+/* test helper: dtw_single() (orc_align) on a bare array of already normalised event means */
+void orc_align_means(const orc_ref_t *ref, const float *means, int32_t n, uint32_t flags, orc_hit_t *hit)
+{
+    orc_event_t *ev = (orc_event_t *)calloc((size_t)(n > 0 ? n : 1), sizeof(orc_event_t));
+    for (int32_t j = 0; j < n; j++)
+        ev[j].mean = means[j];
+    memset(hit, 0, sizeof(*hit));
+    hit->rid = -1;
+    hit->mapped = 1;
+    hit->qstart = 0;
+    hit->qend = n;
+    orc_align(ref, ev, 0, n, flags, hit);
+    free(ev);
+}

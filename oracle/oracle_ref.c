@@ -144,3 +144,32 @@ int32_t orc_ref_len(const orc_ref_t *r, int32_t i) { return r->ref_lengths[i]; }
 int32_t orc_ref_offset(const orc_ref_t *r, int32_t i) { return r->ref_st_offset[i]; }
 const float *orc_ref_fwd(const orc_ref_t *r, int32_t i) { return r->forward[i]; }
 const float *orc_ref_rev(const orc_ref_t *r, int32_t i) { return r->reverse[i]; }
+
+/* test helper: a reference made of caller-given event arrays (flat, back to back), used to
+ * drive orc_align() -- the restatement of dtw_single() -- with arbitrary, e.g. tie-heavy, inputs */
+orc_ref_t *orc_ref_from_events(int32_t num_ref, int32_t has_reverse, const int32_t *lens,
+                               const float *fwd_flat, const float *rev_flat)
+{
+    orc_ref_t *r = (orc_ref_t *)calloc(1, sizeof(orc_ref_t));
+    r->num_ref = num_ref;
+    r->has_reverse = has_reverse;
+    r->ref_lengths = (int32_t *)calloc((size_t)num_ref, sizeof(int32_t));
+    r->ref_seq_lengths = (int32_t *)calloc((size_t)num_ref, sizeof(int32_t));
+    r->ref_st_offset = (int32_t *)calloc((size_t)num_ref, sizeof(int32_t));
+    r->forward = (float **)calloc((size_t)num_ref, sizeof(float *));
+    r->reverse = (float **)calloc((size_t)num_ref, sizeof(float *));
+    size_t at = 0;
+    for (int32_t c = 0; c < num_ref; c++) {
+        const size_t n = (size_t)lens[c];
+        r->ref_lengths[c] = lens[c];
+        r->ref_seq_lengths[c] = lens[c];
+        r->forward[c] = (float *)malloc(sizeof(float) * n);
+        memcpy(r->forward[c], fwd_flat + at, sizeof(float) * n);
+        if (has_reverse) {
+            r->reverse[c] = (float *)malloc(sizeof(float) * n);
+            memcpy(r->reverse[c], rev_flat + at, sizeof(float) * n);
+        }
+        at += n;
+    }
+    return r;
+}

@@ -1,0 +1,379 @@
+// sf_events.cuh -- kernel #1: raw int16 signal -> events -> query window -> z-scored query.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   src/sigfish.c:334-347   pA conversion (event_single)
+//   src/events.c:297-307    compute_sum_sumsq   (fp64 prefix sums, fp32 square)
+//   src/events.c:319-368    compute_tstat       (windows 3/6 DNA, 7/14 RNA)
+//   src/events.c:375-447    short_long_peak_detector
+//   src/events.c:461-508    create_event(s)     (start / length / mean)
+//   src/sigfish.c:424-505   normalise_single    (window [qstart,qend) + z-score)
+//   src/sigfish.c:857-867   query construction  (reversed for RNA unless --invert)
+// The MAD trim of events.c:99-269 has no effect on the reference's results (its return value is
+// dropped at events.c:567) and is not implemented.
+//
+// One read per block.  The signal is consumed in tiles of SF_EV_TILE samples:
+//   1. every thread loads 8 consecutive int16 samples with one 16-byte load and converts to pA;
+//   2. block-wide fp64 scan of (x, x*x) continuing from the previous tile.  Every addition is
+//      checked with TwoSum: when all partial sums are exact the scan equals the reference's
+//      sequential sums bit for bit; a tile with any inexact addition is redone sequentially by
+//      one thread in the reference's order;
+//   3. every thread computes both t-statistics for its positions (32 samples behind the scan so
+//      that the right-hand window is available);
+//   4. one thread runs the two coupled peak finders over the tile (inherently sequential),
+//      closes events as boundaries are emitted and stops the block as soon as the query window
+//      is complete (exact: the detector is causal).
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include "sf_types.cuh"
+
+#define SF_EV_THREADS 128
+#define SF_EV_PER_THREAD 8
+#define SF_EV_TILE (SF_EV_THREADS * SF_EV_PER_THREAD) // 1024 samples
+#define SF_EV_LAG 32                                  // t-stat runs this far behind the scan
+#define SF_EV_KEEP 64                                 // prefix sums kept from the previous tile
+
+struct sf_ev_args {
+    const int16_t *signal;      // all reads of the batch, concatenated (each read 16-byte aligned)
+    const int64_t *sig_off;     // [n_reads + 1] offsets in samples (multiples of 8)
+    const int64_t *sig_len;     // [n_reads]
+    const float *digitisation, *offset, *range; // [n_reads] (already narrowed to fp32, sigfish.c:335-337)
+    int32_t n_reads;
+    uint32_t flags;
+    int32_t q, p;
+    int32_t ev_cap;             // event slots per read in the scratch below (ring when --from-end)
+    uint64_t *ev_start;         // [n_reads][ev_cap]
+    float *ev_mean;             // [n_reads][ev_cap]
+    float *ev_len;              // [n_reads][ev_cap]
+    float *queries;             // [n_reads][q_cap]
+    int32_t q_cap;
+    sf_readinfo *info;          // [n_reads]
+    int32_t keep_all;           // 1: never exit early (event-table dumps for tests)
+};
+
+struct sf_finder {
+    float threshold;
+    unsigned long long window;
+    unsigned long long masked_to;
+    long long peak_pos; // -1: none
+    float peak_val;
+    int valid;
+    double peak_sum; // prefix sum at peak_pos (the event boundary if this peak fires)
+};
+
+__device__ __forceinline__ void sf_finder_reset(sf_finder &f)
+{
+    f.peak_pos = -1;
+    f.peak_val = FLT_MAX;
+    f.valid = 0;
+}
+
+// events.c:343-364 for one position, explicit rounding order
+__device__ __forceinline__ float sf_tstat_at(const double *S, const double *SS, long long i, int w, long long rel)
+{
+    // S/SS are indexed relative: S[k - rel] is the prefix sum of k samples
+    const float wf = (float)w;
+    double lsum = S[i - rel], lsq = SS[i - rel];
+    if (i > w) {
+        lsum = __dsub_rn(lsum, S[i - w - rel]);
+        lsq = __dsub_rn(lsq, SS[i - w - rel]);
+    }
+    const float rsum = __double2float_rn(__dsub_rn(S[i + w - rel], S[i - rel]));
+    const float rsq = __double2float_rn(__dsub_rn(SS[i + w - rel], SS[i - rel]));
+    const float lmean = __double2float_rn(__ddiv_rn(lsum, (double)wf));
+    const float rmean = __fdiv_rn(rsum, wf);
+    const float lmean2 = __fmul_rn(lmean, lmean);
+    const float rmean2 = __fmul_rn(rmean, rmean);
+    const float rq = __fdiv_rn(rsq, wf);
+    double acc = __ddiv_rn(lsq, (double)wf);
+    acc = __dsub_rn(acc, (double)lmean2);
+    acc = __dadd_rn(acc, (double)rq);
+    acc = __dsub_rn(acc, (double)rmean2);
+    float var = __double2float_rn(acc);
+    var = fmaxf(var, FLT_MIN);
+    const float dm = __fsub_rn(rmean, lmean);
+    const float vq = __fdiv_rn(var, wf);
+    return __double2float_rn(__ddiv_rn(fabs((double)dm), __dsqrt_rn((double)vq)));
+}
+
+__device__ __forceinline__ void sf_twosum(double a, double b, double &s, int &inexact)
+{
+    s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    const double err = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    inexact |= (err != 0.0);
+}
+
+__global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_args a)
+{
+    // prefix sums of the samples [rel, rel + KEEP + TILE]; slot j holds S[rel + j]
+    __shared__ double S[SF_EV_KEEP + SF_EV_TILE + 1];
+    __shared__ double SS[SF_EV_KEEP + SF_EV_TILE + 1];
+    __shared__ float T1[SF_EV_TILE + SF_EV_LAG];
+    __shared__ float T2[SF_EV_TILE + SF_EV_LAG];
+    __shared__ double wsum[SF_EV_THREADS / 32], wsq[SF_EV_THREADS / 32];
+    __shared__ int stop_flag;
+
+    const int read = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long n = a.sig_len[read];
+    const int16_t *raw = a.signal + a.sig_off[read];
+    const bool rna = (a.flags & SF_RNA) != 0;
+    const bool from_end = (a.flags & SF_END) != 0;
+    const int w1 = rna ? 7 : 3, w2 = rna ? 14 : 6;
+    const float height = rna ? 1.0f : 0.2f;
+    const float unit = __fdiv_rn(a.range[read], a.digitisation[read]);
+    const float offs = a.offset[read];
+    const int cap = a.ev_cap;
+    uint64_t *ev_start = a.ev_start + (size_t)read * cap;
+    float *ev_mean = a.ev_mean + (size_t)read * cap;
+    float *ev_len = a.ev_len + (size_t)read * cap;
+    // events needed before the block may stop: boundary index qend-1 must exist
+    const long long need_peaks = (from_end || a.keep_all || a.p < 0) ? (1ll << 62) : (long long)a.p + a.q;
+
+    // sequential state (thread 0 only)
+    sf_finder f0, f1;
+    f0.threshold = rna ? 2.5f : 1.4f; f1.threshold = 9.0f;
+    f0.window = w1; f1.window = w2;
+    f0.masked_to = 0; f1.masked_to = 0;
+    f0.peak_sum = 0.0; f1.peak_sum = 0.0;
+    sf_finder_reset(f0); sf_finder_reset(f1);
+    long long npk = 0;
+    unsigned long long prev_b = 0; // start of the open event
+    double prev_s = 0.0;           // prefix sum there
+    int sticky = 0;
+
+    if (tid == 0) {
+        stop_flag = 0;
+        S[SF_EV_KEEP] = 0.0; SS[SF_EV_KEEP] = 0.0; // S[0] for the first tile (rel = -KEEP)
+    }
+    __syncthreads();
+
+    if (n <= 0) {
+        if (tid == 0) {
+            sf_readinfo ri; ri.n_events = 0; ri.qstart = ri.qend = ri.qlen = 0; ri.status = 0; ri.start_raw = ri.end_raw = 0;
+            a.info[read] = ri;
+        }
+        return;
+    }
+
+    const long long n_tiles = (n + SF_EV_TILE - 1) / SF_EV_TILE;
+    for (long long tile = 0; tile < n_tiles; tile++) {
+        const long long base = tile * SF_EV_TILE;  // first sample scanned in this tile
+        const long long rel = base - SF_EV_KEEP;   // sample count of slot 0
+        // ---- 1+2: load, convert, scan ----
+        float xs[SF_EV_PER_THREAD];
+        {
+            const long long i0 = base + (long long)tid * SF_EV_PER_THREAD;
+            union { uint4 pk; int16_t v[SF_EV_PER_THREAD]; } u;
+            if (i0 + SF_EV_PER_THREAD <= n) {
+                u.pk = __ldg(reinterpret_cast<const uint4 *>(raw + i0)); // 8 samples, one 16-byte load
+            } else {
+#pragma unroll
+                for (int k = 0; k < SF_EV_PER_THREAD; k++)
+                    u.v[k] = (i0 + k < n) ? raw[i0 + k] : (int16_t)0;
+            }
+#pragma unroll
+            for (int k = 0; k < SF_EV_PER_THREAD; k++)
+                xs[k] = (i0 + k < n) ? __fmul_rn(__fadd_rn((float)u.v[k], offs), unit) : 0.0f;
+        }
+        int inexact = 0;
+        double ps[SF_EV_PER_THREAD], pq[SF_EV_PER_THREAD];
+        {
+            double acc = 0.0, acq = 0.0;
+#pragma unroll
+            for (int k = 0; k < SF_EV_PER_THREAD; k++) {
+                sf_twosum(acc, (double)xs[k], acc, inexact);
+                sf_twosum(acq, (double)__fmul_rn(xs[k], xs[k]), acq, inexact);
+                ps[k] = acc; pq[k] = acq;
+            }
+        }
+        // warp-inclusive scan of the thread totals
+        double tot = ps[SF_EV_PER_THREAD - 1], toq = pq[SF_EV_PER_THREAD - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double us = __shfl_up_sync(0xffffffffu, tot, o);
+            const double uq = __shfl_up_sync(0xffffffffu, toq, o);
+            if (lane >= o) {
+                sf_twosum(tot, us, tot, inexact);
+                sf_twosum(toq, uq, toq, inexact);
+            }
+        }
+        if (lane == 31) { wsum[warp] = tot; wsq[warp] = toq; }
+        __syncthreads();
+        double carry = S[SF_EV_KEEP], carq = SS[SF_EV_KEEP]; // prefix sum at `base`
+        for (int wv = 0; wv < warp; wv++) {
+            sf_twosum(carry, wsum[wv], carry, inexact);
+            sf_twosum(carq, wsq[wv], carq, inexact);
+        }
+        // exclusive prefix of this thread = carry + (tot - own total) -> take it from the lane below
+        double exs = __shfl_up_sync(0xffffffffu, tot, 1), exq = __shfl_up_sync(0xffffffffu, toq, 1);
+        if (lane == 0) { exs = 0.0; exq = 0.0; }
+        sf_twosum(carry, exs, carry, inexact);
+        sf_twosum(carq, exq, carq, inexact);
+#pragma unroll
+        for (int k = 0; k < SF_EV_PER_THREAD; k++) {
+            double vs, vq;
+            sf_twosum(carry, ps[k], vs, inexact);
+            sf_twosum(carq, pq[k], vq, inexact);
+            const int slot = SF_EV_KEEP + 1 + tid * SF_EV_PER_THREAD + k;
+            S[slot] = vs; SS[slot] = vq;
+        }
+        const int any_inexact = __syncthreads_or(inexact);
+        if (any_inexact) {
+            // redo this tile in the reference's order (events.c:303-306); needs the pA values again
+            if (tid == 0) {
+                double acc = S[SF_EV_KEEP], acq = SS[SF_EV_KEEP];
+                const long long lim = min((long long)SF_EV_TILE, n - base);
+                for (long long k = 0; k < lim; k++) {
+                    const float x = __fmul_rn(__fadd_rn((float)raw[base + k], offs), unit);
+                    acc = __dadd_rn(acc, (double)x);
+                    acq = __dadd_rn(acq, (double)__fmul_rn(x, x));
+                    S[SF_EV_KEEP + 1 + k] = acc; SS[SF_EV_KEEP + 1 + k] = acq;
+                }
+                sticky = 1;
+            }
+            __syncthreads();
+        }
+
+        // ---- 3: t-statistics for positions [base - LAG, hi_pos) ----
+        const long long scanned = min(base + SF_EV_TILE, n); // prefix sums known up to S[scanned]
+        const long long lo_pos = base - SF_EV_LAG < 0 ? 0 : base - SF_EV_LAG;
+        const long long hi_pos = (scanned >= n) ? n : base + SF_EV_TILE - SF_EV_LAG;
+        for (long long i = lo_pos + tid; i < hi_pos; i += SF_EV_THREADS) {
+            float t1 = 0.0f, t2 = 0.0f;
+            if (n >= 2 * w1 && i >= w1 && i <= n - w1) t1 = sf_tstat_at(S, SS, i, w1, rel);
+            if (n >= 2 * w2 && i >= w2 && i <= n - w2) t2 = sf_tstat_at(S, SS, i, w2, rel);
+            T1[i - lo_pos] = t1; T2[i - lo_pos] = t2;
+        }
+        __syncthreads();
+
+        // ---- 4: sequential peak finders + event closing (thread 0) ----
+        if (tid == 0) {
+            for (long long i = lo_pos; i < hi_pos; i++) {
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    sf_finder &me = d == 0 ? f0 : f1;
+                    if (me.masked_to >= (unsigned long long)i)
+                        continue;
+                    const float v = d == 0 ? T1[i - lo_pos] : T2[i - lo_pos];
+                    if (me.peak_pos < 0) {
+                        if (v < me.peak_val) {
+                            me.peak_val = v;
+                        } else if (__fsub_rn(v, me.peak_val) > height) {
+                            me.peak_val = v;
+                            me.peak_pos = i;
+                            me.peak_sum = S[i - rel];
+                        }
+                        continue;
+                    }
+                    if (v > me.peak_val) {
+                        me.peak_val = v;
+                        me.peak_pos = i;
+                        me.peak_sum = S[i - rel];
+                    }
+                    if (d == 0 && me.peak_val > me.threshold) {
+                        f1.masked_to = (unsigned long long)me.peak_pos + me.window;
+                        sf_finder_reset(f1);
+                    }
+                    if (__fsub_rn(me.peak_val, v) > height && me.peak_val > me.threshold)
+                        me.valid = 1;
+                    if (me.valid && ((unsigned long long)i - (unsigned long long)me.peak_pos) > me.window / 2) {
+                        // boundary at peak_pos closes the open event (events.c:461-477)
+                        const unsigned long long b = (unsigned long long)me.peak_pos;
+                        const float len = (float)(b - prev_b);
+                        const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(me.peak_sum, prev_s)), len);
+                        const long long slot = npk % cap;
+                        ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                        npk++;
+                        prev_b = b; prev_s = me.peak_sum;
+                        me.peak_pos = -1;
+                        me.peak_val = v;
+                        me.valid = 0;
+                    }
+                }
+                if (npk >= need_peaks) {
+                    stop_flag = 1;
+                    break;
+                }
+            }
+        }
+        // keep the last KEEP+1 prefix sums for the next tile
+        __syncthreads();
+        if (stop_flag)
+            break;
+        double ks = 0.0, kq = 0.0;
+        if (tid <= SF_EV_KEEP) { ks = S[SF_EV_TILE + tid]; kq = SS[SF_EV_TILE + tid]; }
+        __syncthreads();
+        if (tid <= SF_EV_KEEP) { S[tid] = ks; SS[tid] = kq; }
+        __syncthreads();
+    }
+
+    // ---- window + z-score + query (thread 0; fp32 sums in the reference's order) ----
+    if (tid == 0) {
+        sf_readinfo ri;
+        ri.status = sticky ? 8 : 0;
+        long long nev;
+        if (stop_flag) {
+            nev = npk + 1; // lower bound; only compared against qend, which it exceeds
+        } else if (npk == 0) {
+            nev = 0;       // the reference reads peaks[-1] here (events.c:504): undefined
+            ri.status |= 4;
+        } else {
+            // last event runs to the end of the signal (events.c:503-505); S[n] is in the last tile
+            const long long rel = (n_tiles - 1) * SF_EV_TILE - SF_EV_KEEP;
+            const float len = (float)((unsigned long long)n - prev_b);
+            const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(S[n - rel], prev_s)), len);
+            const long long slot = npk % cap;
+            ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+            nev = npk + 1;
+        }
+        ri.n_events = nev;
+        long long lo = 0, hi = 0, nn = nev;
+        if (nn > 0) {
+            if (!from_end) { // sigfish.c:435-462
+                lo = a.p < 0 ? 50 : a.p;
+                hi = lo + a.q;
+                if (lo + 25 > nn) { lo = hi = 0; nn = 0; ri.status |= 1; }
+                else if (hi > nn) { hi = nn; ri.status |= 2; }
+            } else {         // sigfish.c:464-478
+                lo = nn - a.p - a.q;
+                hi = nn - a.p;
+                if (lo < 0) { lo = 0; ri.status |= 2; }
+                if (hi < 0) { hi = 0; nn = 0; ri.status |= 1; }
+            }
+        }
+        ri.qstart = (int)lo; ri.qend = (int)hi;
+        int qlen = nn > 0 ? (int)(hi - lo) : 0;
+        if (qlen > a.q_cap) qlen = 0; // cannot happen (hi - lo <= q)
+        ri.qlen = qlen;
+        ri.start_raw = 0; ri.end_raw = 0;
+        if (qlen > 0) {
+            // sigfish.c:483-502
+            const float cnt = (float)qlen;
+            float mean = 0.0f;
+            for (long long j = lo; j < hi; j++) mean = __fadd_rn(mean, ev_mean[j % cap]);
+            mean = __fdiv_rn(mean, cnt);
+            float var = 0.0f;
+            for (long long j = lo; j < hi; j++) {
+                const float d = __fsub_rn(ev_mean[j % cap], mean);
+                var = __fadd_rn(var, __fmul_rn(d, d));
+            }
+            var = __fdiv_rn(var, cnt);
+            const float sd = __fsqrt_rn(var);
+            float *qv = a.queries + (size_t)read * a.q_cap;
+            const bool flip = rna && !(a.flags & SF_INV); // sigfish.c:857-867
+            for (long long j = lo; j < hi; j++) {
+                const float z = __fdiv_rn(__fsub_rn(ev_mean[j % cap], mean), sd);
+                const int k = (int)(j - lo);
+                qv[flip ? qlen - 1 - k : k] = z;
+            }
+            // sigfish.c:804-805 (uint64 + float evaluates in fp32)
+            ri.start_raw = ev_start[lo % cap];
+            const long long le = hi - 1;
+            ri.end_raw = (uint64_t)__fadd_rn((float)ev_start[le % cap], ev_len[le % cap]);
+        }
+        a.info[read] = ri;
+    }
+}

@@ -1,0 +1,993 @@
+// sfgpu.cu -- libsfgpu.so: the C-ABI of include/sfgpu.h over the sm_100a kernels in this directory.
+//
+// Host-side responsibilities (everything else is in the kernels):
+//   * reference layout: segments in the reference's processing order (sigfish.c:870,890,936),
+//     each preceded by a +INF sentinel column, packed into groups that one warp streams through;
+//   * batch slots: pinned staging + device buffers + one CUDA stream per slot, so that the copy of
+//     batch n+1 overlaps the kernels of batch n (this replaces the pthread fan-out of thread.c);
+//   * launch order per batch: H2D -> events -> DTW scores -> merge + start coordinate -> D2H.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/sfgpu.h"
+#include "sf_types.cuh"
+#include "sf_events.cuh"
+#include "sf_ref.cuh"
+#include "sf_dtw.cuh"
+#include "sf_trace.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+struct sf_slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // capacities
+    int32_t cap_reads = 0;
+    int64_t cap_samples = 0;
+    // host pinned
+    int16_t *h_signal = nullptr;
+    int64_t *h_off = nullptr; // [cap_reads + 1] padded offsets, then [cap_reads] lengths
+    float *h_scal = nullptr;  // [3][cap_reads]
+    float *h_queries = nullptr; // only for sfgpu_submit_queries
+    bool queries_only = false;
+    sf_readinfo *h_info = nullptr;
+    sf_hit *h_hits = nullptr;
+    // device
+    int16_t *d_signal = nullptr;
+    int64_t *d_off = nullptr;
+    float *d_scal = nullptr;
+    uint64_t *d_ev_start = nullptr;
+    float *d_ev_mean = nullptr, *d_ev_len = nullptr;
+    float *d_queries = nullptr;
+    sf_readinfo *d_info = nullptr;
+    sf_taskres *d_res = nullptr;
+    float *d_ckpt = nullptr;
+    sf_hit *d_hits = nullptr;
+    unsigned int *d_counter = nullptr;
+    // state
+    int32_t n_reads = 0;
+    int64_t n_samples = 0; // padded
+    int64_t raw_samples = 0;
+    bool busy = false, done = false, timed = false;
+    sfgpu_timing_t timing;
+};
+
+} // namespace
+
+struct sfgpu_ctx {
+    sfgpu_opt_t opt;
+    int R = 0, q_cap = 0, ev_cap = 0;
+    int sm_count = 0;
+    float *d_level_mean = nullptr;
+    // reference
+    bool have_ref = false;
+    int32_t num_ref = 0, n_seg = 0, n_groups = 0;
+    std::vector<sf_seg> segs;
+    std::vector<sf_group> groups;
+    std::vector<int32_t> seg_group, order, ref_lengths;
+    float *d_stream = nullptr;
+    int64_t stream_len = 0;
+    sf_seg *d_segs = nullptr;
+    sf_group *d_groups = nullptr;
+    int32_t *d_order = nullptr, *d_seg_group = nullptr;
+    int64_t ck_per_read = 0, ref_columns = 0;
+    int32_t min_window = 0;
+    int32_t ck_min_cols = 8192; // segments longer than this get wavefront checkpoints (reserved[0] overrides)
+    std::vector<sf_slot> slots;
+    int dtw_blocks_per_sm = 0;
+    char err[512];
+};
+
+namespace {
+
+int fail(sfgpu_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    if (c)
+        memcpy(c->err, g_err, sizeof g_err);
+    return code;
+}
+
+#define SF_CUDA(c, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail((c), SFGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,              \
+                        cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+const int kRows[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+
+int pick_rows(int q)
+{
+    const int need = (q + 31) / 32;
+    for (int r : kRows)
+        if (r >= need)
+            return r;
+    return 0;
+}
+
+template <typename T> void dfree(T *&p)
+{
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+}
+template <typename T> void hfree(T *&p)
+{
+    if (p)
+        cudaFreeHost(p);
+    p = nullptr;
+}
+
+void slot_free_buffers(sf_slot &s)
+{
+    hfree(s.h_signal); hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
+    dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
+    dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
+    dfree(s.d_hits);
+    s.cap_reads = 0;
+    s.cap_samples = 0;
+}
+
+int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
+{
+    if (n_samples > s.cap_samples) {
+        const int64_t cap = std::max<int64_t>(n_samples + n_samples / 4, 1 << 20);
+        hfree(s.h_signal);
+        dfree(s.d_signal);
+        s.cap_samples = 0;
+        SF_CUDA(c, cudaMallocHost(&s.h_signal, sizeof(int16_t) * cap));
+        SF_CUDA(c, cudaMalloc(&s.d_signal, sizeof(int16_t) * cap));
+        s.cap_samples = cap;
+    }
+    if (n_reads > s.cap_reads) {
+        const int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
+        hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
+        dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
+        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits);
+        s.cap_reads = 0;
+        const size_t n = (size_t)cap;
+        SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
+        SF_CUDA(c, cudaMallocHost(&s.h_scal, sizeof(float) * 3 * n));
+        SF_CUDA(c, cudaMallocHost(&s.h_info, sizeof(sf_readinfo) * n));
+        SF_CUDA(c, cudaMallocHost(&s.h_hits, sizeof(sf_hit) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_off, sizeof(int64_t) * (2 * n + 1)));
+        SF_CUDA(c, cudaMalloc(&s.d_scal, sizeof(float) * 3 * n));
+        SF_CUDA(c, cudaMalloc(&s.d_ev_start, sizeof(uint64_t) * n * c->ev_cap));
+        SF_CUDA(c, cudaMalloc(&s.d_ev_mean, sizeof(float) * n * c->ev_cap));
+        SF_CUDA(c, cudaMalloc(&s.d_ev_len, sizeof(float) * n * c->ev_cap));
+        SF_CUDA(c, cudaMalloc(&s.d_queries, sizeof(float) * n * c->q_cap));
+        SF_CUDA(c, cudaMalloc(&s.d_info, sizeof(sf_readinfo) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_res, sizeof(sf_taskres) * n * std::max(1, c->n_groups)));
+        if (c->ck_per_read > 0)
+            SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)((c->R + 1) * 32)));
+        SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
+        s.cap_reads = cap;
+    }
+    return SFGPU_OK;
+}
+
+// ---- kernel dispatch over the register tile height R and the recurrence variant ----
+
+template <int R, bool STD> int dtw_occupancy(size_t smem)
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_score_kernel<R, STD>, SF_DTW_THREADS, smem);
+    return nb;
+}
+
+template <int R, bool STD>
+cudaError_t launch_dtw(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
+{
+    sf_dtw_score_kernel<R, STD><<<grid, SF_DTW_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cudaStream_t st)
+{
+    const int warps = 4;
+    const int grid = (a.n_reads + warps - 1) / warps;
+    sf_trace_kernel<R, STD><<<grid, warps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define SF_DISPATCH_R(R_, STD_, EXPR)                                                             \
+    switch (R_) {                                                                                 \
+    case 1: { constexpr int R = 1; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 2: { constexpr int R = 2; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 3: { constexpr int R = 3; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 4: { constexpr int R = 4; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 5: { constexpr int R = 5; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 6: { constexpr int R = 6; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 7: { constexpr int R = 7; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 8: { constexpr int R = 8; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 10: { constexpr int R = 10; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 12: { constexpr int R = 12; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 16: { constexpr int R = 16; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 20: { constexpr int R = 20; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 24: { constexpr int R = 24; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    case 32: { constexpr int R = 32; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
+    default: break;                                                                               \
+    }
+
+// the device stages of one batch, on the slot's stream
+int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
+{
+    const int n = s.n_reads;
+    const bool std_dtw = (c->opt.flags & SFGPU_DTW) != 0;
+    cudaStream_t st = s.stream;
+    SF_CUDA(c, cudaEventRecord(s.ev[0], st));
+    if (with_h2d && n > 0 && !with_events) {
+        SF_CUDA(c, cudaMemcpyAsync(s.d_queries, s.h_queries, sizeof(float) * (size_t)n * c->q_cap, cudaMemcpyHostToDevice, st));
+        SF_CUDA(c, cudaMemcpyAsync(s.d_info, s.h_info, sizeof(sf_readinfo) * n, cudaMemcpyHostToDevice, st));
+    }
+    if (with_h2d && n > 0 && with_events) {
+        SF_CUDA(c, cudaMemcpyAsync(s.d_signal, s.h_signal, sizeof(int16_t) * s.n_samples, cudaMemcpyHostToDevice, st));
+        SF_CUDA(c, cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * (2 * (size_t)n + 1), cudaMemcpyHostToDevice, st));
+        SF_CUDA(c, cudaMemcpyAsync(s.d_scal, s.h_scal, sizeof(float) * 3 * (size_t)s.cap_reads, cudaMemcpyHostToDevice, st));
+    }
+    SF_CUDA(c, cudaEventRecord(s.ev[1], st));
+    s.timing.dtw_launches = 0;
+    s.timing.other_launches = 0;
+    if (n > 0 && with_events) {
+        sf_ev_args ea;
+        ea.signal = s.d_signal;
+        ea.sig_off = s.d_off;
+        ea.sig_len = s.d_off + (n + 1);
+        ea.digitisation = s.d_scal;
+        ea.offset = s.d_scal + s.cap_reads;
+        ea.range = s.d_scal + 2 * (size_t)s.cap_reads;
+        ea.n_reads = n;
+        ea.flags = c->opt.flags;
+        ea.q = c->opt.query_size;
+        ea.p = c->opt.prefix_size;
+        ea.ev_cap = c->ev_cap;
+        ea.ev_start = s.d_ev_start;
+        ea.ev_mean = s.d_ev_mean;
+        ea.ev_len = s.d_ev_len;
+        ea.queries = s.d_queries;
+        ea.q_cap = c->q_cap;
+        ea.info = s.d_info;
+        ea.keep_all = 0;
+        sf_events_kernel<<<n, SF_EV_THREADS, 0, st>>>(ea);
+        SF_CUDA(c, cudaGetLastError());
+        s.timing.other_launches++;
+    }
+    SF_CUDA(c, cudaEventRecord(s.ev[2], st));
+    if (n > 0) {
+        SF_CUDA(c, cudaMemsetAsync(s.d_counter, 0, sizeof(unsigned int), st));
+        sf_dtw_args da;
+        da.stream = c->d_stream;
+        da.segs = c->d_segs;
+        da.groups = c->d_groups;
+        da.order = c->d_order;
+        da.n_groups = c->n_groups;
+        da.n_reads = n;
+        da.queries = s.d_queries;
+        da.info = s.d_info;
+        da.q_cap = c->q_cap;
+        da.res = s.d_res;
+        da.ckpt = s.d_ckpt;
+        da.ck_per_read = c->ck_per_read;
+        da.counter = s.d_counter;
+        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(c->R);
+        const long long n_tasks = (long long)n * c->n_groups;
+        const long long want = (n_tasks + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * c->dtw_blocks_per_sm));
+        cudaError_t e = cudaErrorInvalidValue;
+        SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(da, grid, smem, st)));
+        SF_CUDA(c, e);
+        s.timing.dtw_launches++;
+    }
+    SF_CUDA(c, cudaEventRecord(s.ev[3], st));
+    if (n > 0) {
+        sf_trace_args ta;
+        ta.stream = c->d_stream;
+        ta.segs = c->d_segs;
+        ta.groups = c->d_groups;
+        ta.seg_group = c->d_seg_group;
+        ta.n_groups = c->n_groups;
+        ta.n_reads = n;
+        ta.queries = s.d_queries;
+        ta.info = s.d_info;
+        ta.q_cap = c->q_cap;
+        ta.res = s.d_res;
+        ta.ckpt = s.d_ckpt;
+        ta.ck_per_read = c->ck_per_read;
+        ta.hits = s.d_hits;
+        ta.min_window = c->min_window;
+        cudaError_t e = cudaErrorInvalidValue;
+        SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st)));
+        SF_CUDA(c, e);
+        s.timing.other_launches++;
+    }
+    SF_CUDA(c, cudaEventRecord(s.ev[4], st));
+    if (n > 0) {
+        SF_CUDA(c, cudaMemcpyAsync(s.h_info, s.d_info, sizeof(sf_readinfo) * n, cudaMemcpyDeviceToHost, st));
+        SF_CUDA(c, cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(sf_hit) * n, cudaMemcpyDeviceToHost, st));
+    }
+    SF_CUDA(c, cudaEventRecord(s.ev[5], st));
+    s.busy = true;
+    s.done = false;
+    s.timed = false;
+    return SFGPU_OK;
+}
+
+int slot_wait(sfgpu_ctx *c, sf_slot &s)
+{
+    if (!s.busy)
+        return SFGPU_OK;
+    SF_CUDA(c, cudaStreamSynchronize(s.stream));
+    s.busy = false;
+    s.done = true;
+    if (!s.timed) {
+        float ms[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 5; i++)
+            SF_CUDA(c, cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
+        s.timing.h2d_ms = ms[0];
+        s.timing.events_ms = ms[1];
+        s.timing.dtw_ms = ms[2];
+        s.timing.trace_ms = ms[3];
+        s.timing.d2h_ms = ms[4];
+        s.timing.total_ms = ms[0] + ms[1] + ms[2] + ms[3] + ms[4];
+        double cells = 0.0;
+        for (int i = 0; i < s.n_reads; i++)
+            cells += (double)s.h_info[i].qlen * (double)c->ref_columns;
+        s.timing.cells = cells;
+        s.timing.samples = s.raw_samples;
+        s.timed = true;
+    }
+    return SFGPU_OK;
+}
+
+void free_ref(sfgpu_ctx *c)
+{
+    dfree(c->d_stream); dfree(c->d_segs); dfree(c->d_groups); dfree(c->d_order); dfree(c->d_seg_group);
+    c->have_ref = false;
+}
+
+// waits for all slots, releases their buffers (group count / checkpoint layout may change) and the
+// resident reference
+int drop_ref(sfgpu_ctx *c)
+{
+    for (auto &s : c->slots) {
+        int rc = slot_wait(c, s);
+        if (rc)
+            return rc;
+        slot_free_buffers(s);
+        s.done = false;
+    }
+    free_ref(c);
+    return SFGPU_OK;
+}
+
+// Lays the segments out in the reference's processing order (contig ascending, '+' then '-':
+// sigfish.c:870,890,936), one +INF sentinel column in front of each, packs them into groups and
+// allocates the stream (filled with +INF).
+int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_reverse)
+{
+    c->segs.clear();
+    c->ref_lengths.assign(rlens, rlens + num_ref);
+    int64_t pos = 0; // stream cursor
+    for (int32_t r = 0; r < num_ref; r++) {
+        for (int strand = 0; strand < (has_reverse ? 2 : 1); strand++) {
+            sf_seg sg;
+            sg.off = pos + 1; // sentinel at pos
+            sg.rlen = rlens[r];
+            sg.rid = r;
+            sg.strand = strand;
+            sg.pad = 0;
+            c->segs.push_back(sg);
+            pos += (int64_t)rlens[r] + 1;
+        }
+    }
+    c->num_ref = num_ref;
+    c->n_seg = (int32_t)c->segs.size();
+    c->stream_len = pos + 64;
+    c->ref_columns = 0;
+    for (const auto &sg : c->segs)
+        c->ref_columns += sg.rlen;
+
+    // ---- groups: consecutive segments up to a column budget ----
+    const int64_t budget = std::max<int64_t>(4096, std::min<int64_t>(65536, c->ref_columns / 64));
+    c->groups.clear();
+    c->seg_group.assign(c->n_seg, 0);
+    int s0 = 0;
+    while (s0 < c->n_seg) {
+        int s1 = s0;
+        int64_t cols = 0;
+        int32_t longest = 0;
+        while (s1 < c->n_seg && (s1 == s0 || cols + c->segs[s1].rlen + 1 <= budget)) {
+            cols += c->segs[s1].rlen + 1;
+            longest = std::max(longest, c->segs[s1].rlen);
+            s1++;
+        }
+        sf_group g;
+        g.begin = c->segs[s0].off - 1;
+        g.end = c->segs[s1 - 1].off + c->segs[s1 - 1].rlen;
+        g.seg0 = s0;
+        g.nseg = s1 - s0;
+        g.ck_every = 0;
+        g.n_ck = 0;
+        g.ck_prefix = 0;
+        if (g.end - g.begin > 0x7ffffff0ll)
+            return fail(c, SFGPU_ELIMIT, "segment group too long");
+        if (longest > c->ck_min_cols) {
+            // checkpoint period: ~1/512 of the segment, clamped
+            const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, std::min<int64_t>(8192, longest / 512));
+            g.ck_every = (int32_t)((cols_per + 31) / 32);
+            g.n_ck = (int32_t)(((g.end - g.begin) / 32) / g.ck_every);
+        }
+        for (int s = s0; s < s1; s++)
+            c->seg_group[s] = (int32_t)c->groups.size();
+        c->groups.push_back(g);
+        s0 = s1;
+    }
+    c->n_groups = (int32_t)c->groups.size();
+    c->ck_per_read = 0;
+    for (auto &g : c->groups) {
+        g.ck_prefix = c->ck_per_read;
+        c->ck_per_read += g.n_ck;
+    }
+    c->order.resize(c->n_groups);
+    for (int i = 0; i < c->n_groups; i++)
+        c->order[i] = i;
+    std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b) {
+        return (c->groups[a].end - c->groups[a].begin) > (c->groups[b].end - c->groups[b].begin);
+    });
+
+    SF_CUDA(c, cudaMalloc(&c->d_stream, sizeof(float) * c->stream_len));
+    SF_CUDA(c, cudaMalloc(&c->d_segs, sizeof(sf_seg) * c->n_seg));
+    SF_CUDA(c, cudaMemcpy(c->d_segs, c->segs.data(), sizeof(sf_seg) * c->n_seg, cudaMemcpyHostToDevice));
+    SF_CUDA(c, cudaMalloc(&c->d_groups, sizeof(sf_group) * c->n_groups));
+    SF_CUDA(c, cudaMemcpy(c->d_groups, c->groups.data(), sizeof(sf_group) * c->n_groups, cudaMemcpyHostToDevice));
+    SF_CUDA(c, cudaMalloc(&c->d_order, sizeof(int32_t) * c->n_groups));
+    SF_CUDA(c, cudaMemcpy(c->d_order, c->order.data(), sizeof(int32_t) * c->n_groups, cudaMemcpyHostToDevice));
+    SF_CUDA(c, cudaMalloc(&c->d_seg_group, sizeof(int32_t) * c->n_seg));
+    SF_CUDA(c, cudaMemcpy(c->d_seg_group, c->seg_group.data(), sizeof(int32_t) * c->n_seg, cudaMemcpyHostToDevice));
+    sf_fill_inf_kernel<<<c->sm_count * 4, 256>>>(c->d_stream, (size_t)c->stream_len);
+    SF_CUDA(c, cudaGetLastError());
+    SF_CUDA(c, cudaDeviceSynchronize());
+    return SFGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sfgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10)
+            ok++;
+    }
+    return ok;
+}
+
+const char *sfgpu_strerror(const sfgpu_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mean)
+{
+    if (!out || !opt || !level_mean)
+        return fail(nullptr, SFGPU_EARG, "sfgpu_create: null argument");
+    *out = nullptr;
+    if (opt->query_size <= 0)
+        return fail(nullptr, SFGPU_EARG, "query_size must be positive");
+    if (opt->prefix_size < 0)
+        return fail(nullptr, SFGPU_EARG, "prefix_size < 0 (auto query start) is resolved by the host before the device stages");
+    if (opt->kmer_size < 1 || opt->kmer_size > 12)
+        return fail(nullptr, SFGPU_EARG, "kmer_size out of range");
+    const int rows = pick_rows(opt->query_size);
+    if (rows == 0)
+        return fail(nullptr, SFGPU_ELIMIT, "query_size %d exceeds the supported maximum of 1024 events", opt->query_size);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, SFGPU_ENODEV, "no CUDA device (this library has no CPU fallback)");
+    if (opt->device < 0 || opt->device >= ndev)
+        return fail(nullptr, SFGPU_EARG, "device %d out of range (%d present)", opt->device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, opt->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, SFGPU_ENODEV, "device %d is not an sm_100 GPU (kernels are built for sm_100a only)", opt->device);
+
+    sfgpu_ctx *c = new (std::nothrow) sfgpu_ctx();
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "out of host memory");
+    c->err[0] = 0;
+    c->opt = *opt;
+    c->R = rows;
+    c->q_cap = 32 * rows;
+    c->ev_cap = opt->prefix_size + opt->query_size + 4;
+    c->sm_count = prop.multiProcessorCount;
+    c->min_window = 2 * opt->query_size;
+    if (opt->reserved[0] > 0)
+        c->ck_min_cols = std::max(128, opt->reserved[0]);
+    if (opt->reserved[1] > 0)
+        c->min_window = opt->reserved[1];
+    if (c->opt.n_slots <= 0)
+        c->opt.n_slots = 2;
+    int rc = [&]() -> int {
+        SF_CUDA(c, cudaSetDevice(opt->device));
+        const size_t nm = (size_t)1 << (2 * opt->kmer_size);
+        SF_CUDA(c, cudaMalloc(&c->d_level_mean, sizeof(float) * nm));
+        SF_CUDA(c, cudaMemcpy(c->d_level_mean, level_mean, sizeof(float) * nm, cudaMemcpyHostToDevice));
+        c->slots.resize(c->opt.n_slots);
+        for (auto &s : c->slots) {
+            SF_CUDA(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            for (auto &e : s.ev)
+                SF_CUDA(c, cudaEventCreate(&e));
+            SF_CUDA(c, cudaMalloc(&s.d_counter, sizeof(unsigned int)));
+            memset(&s.timing, 0, sizeof s.timing);
+        }
+        const bool std_dtw = (opt->flags & SFGPU_DTW) != 0;
+        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(rows);
+        int nb = 0;
+        SF_DISPATCH_R(rows, std_dtw, (nb = dtw_occupancy<R, STD>(smem)));
+        if (nb <= 0)
+            return fail(c, SFGPU_ECUDA, "DTW kernel does not fit on the device (R=%d)", rows);
+        c->dtw_blocks_per_sm = nb;
+        return SFGPU_OK;
+    }();
+    if (rc != SFGPU_OK) {
+        char keep[512];
+        memcpy(keep, c->err, sizeof keep);
+        sfgpu_destroy(c);
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
+    *out = c;
+    return SFGPU_OK;
+}
+
+void sfgpu_destroy(sfgpu_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->opt.device);
+    for (auto &s : c->slots) {
+        if (s.stream)
+            cudaStreamSynchronize(s.stream);
+        slot_free_buffers(s);
+        dfree(s.d_counter);
+        for (auto &e : s.ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (s.stream)
+            cudaStreamDestroy(s.stream);
+    }
+    free_ref(c);
+    dfree(c->d_level_mean);
+    delete c;
+}
+
+int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_t *base_off,
+                  int32_t *ref_lengths, int32_t *ref_seq_lengths, int32_t *ref_st_offset)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (num_ref <= 0 || !bases || !base_off)
+        return fail(c, SFGPU_EARG, "sfgpu_set_ref: empty reference");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    int rc = drop_ref(c);
+    if (rc)
+        return rc;
+
+    const uint32_t flags = c->opt.flags;
+    const bool rna = (flags & SFGPU_RNA) != 0;
+    const int k = c->opt.kmer_size;
+    const int q = c->opt.query_size;
+    std::vector<sf_refseg> rsegs;
+    std::vector<int32_t> rlens(num_ref);
+    for (int32_t r = 0; r < num_ref; r++) {
+        const int64_t l64 = base_off[r + 1] - base_off[r];
+        if (l64 < k || l64 > 0x7fffff00ll)
+            return fail(c, SFGPU_EARG, "contig %d has %lld bases; need between k=%d and 2^31", r, (long long)l64, k);
+        const int32_t l = (int32_t)l64;
+        const int32_t nk = l + 1 - k;
+        // genref.c:128-136: DNA and --full-ref use every k-mer, RNA the 1.5*q nearest one end
+        int32_t rl = nk;
+        if (rna && !(flags & SFGPU_REF)) {
+            const uint32_t cap = (uint32_t)(q * 1.5);
+            rl = cap > (uint32_t)nk ? nk : (int32_t)cap;
+        }
+        int32_t st_off = 0;
+        sf_refseg f;
+        f.base_off = base_off[r];
+        f.seq_len = l;
+        f.first = 0;
+        f.mode = 0;
+        f.pad = 0;
+        if (rna) {
+            if (flags & SFGPU_INV) {          // genref.c:166-177 (offset left at 0)
+                f.first = l - rl - (k - 1);
+                f.mode = 2;
+            } else if (!(flags & SFGPU_END)) { // genref.c:185-197
+                st_off = l - rl - (k - 1);
+                f.first = st_off;
+            }
+        }
+        rlens[r] = rl;
+        if (ref_lengths) ref_lengths[r] = rl;
+        if (ref_seq_lengths) ref_seq_lengths[r] = l;
+        if (ref_st_offset) ref_st_offset[r] = st_off;
+        rsegs.push_back(f);
+        if (!rna) {
+            f.mode = 1;
+            rsegs.push_back(f);
+        }
+    }
+    rc = layout_ref(c, num_ref, rlens.data(), !rna);
+    if (rc)
+        return rc;
+
+    const int64_t n_bases = base_off[num_ref];
+    uint8_t *d_bases = nullptr;
+    sf_refseg *d_rseg = nullptr;
+    float2 *d_stats = nullptr;
+    rc = [&]() -> int {
+        SF_CUDA(c, cudaMalloc(&d_bases, (size_t)n_bases + 16));
+        SF_CUDA(c, cudaMemcpy(d_bases, bases, (size_t)n_bases, cudaMemcpyHostToDevice));
+        SF_CUDA(c, cudaMalloc(&d_rseg, sizeof(sf_refseg) * c->n_seg));
+        SF_CUDA(c, cudaMemcpy(d_rseg, rsegs.data(), sizeof(sf_refseg) * c->n_seg, cudaMemcpyHostToDevice));
+        SF_CUDA(c, cudaMalloc(&d_stats, sizeof(float2) * c->n_seg));
+        sf_ref_args ra;
+        ra.bases = d_bases;
+        ra.rseg = d_rseg;
+        ra.segs = c->d_segs;
+        ra.n_seg = c->n_seg;
+        ra.level_mean = c->d_level_mean;
+        ra.k = k;
+        ra.stream = c->d_stream;
+        ra.stats = d_stats;
+        int32_t longest = 0;
+        for (const auto &sg : c->segs)
+            longest = std::max(longest, sg.rlen);
+        dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 2, (longest + 255) / 256)),
+                  (unsigned)std::min(c->n_seg, 32768));
+        sf_ref_fill_kernel<<<grid, 256>>>(ra);
+        SF_CUDA(c, cudaGetLastError());
+        const int stat_blocks = std::max(1, std::min((c->n_seg + 3) / 4, c->sm_count * 8));
+        sf_ref_stats_kernel<<<stat_blocks, 128>>>(ra);
+        SF_CUDA(c, cudaGetLastError());
+        sf_ref_scale_kernel<<<grid, 256>>>(ra);
+        SF_CUDA(c, cudaGetLastError());
+        SF_CUDA(c, cudaDeviceSynchronize());
+        return SFGPU_OK;
+    }();
+    dfree(d_bases);
+    dfree(d_rseg);
+    dfree(d_stats);
+    if (rc != SFGPU_OK) {
+        free_ref(c);
+        return rc;
+    }
+    c->have_ref = true;
+    return SFGPU_OK;
+}
+
+int sfgpu_set_ref_events(sfgpu_ctx *c, int32_t num_ref, int32_t has_reverse, const float *events,
+                         const int64_t *ev_off)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (num_ref <= 0 || !events || !ev_off)
+        return fail(c, SFGPU_EARG, "sfgpu_set_ref_events: empty reference");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    int rc = drop_ref(c);
+    if (rc)
+        return rc;
+    const int per = has_reverse ? 2 : 1;
+    std::vector<int32_t> rlens(num_ref);
+    for (int32_t r = 0; r < num_ref; r++) {
+        const int64_t l = ev_off[per * r + 1] - ev_off[per * r];
+        if (l <= 0 || l > 0x7fffff00ll || (has_reverse && ev_off[2 * r + 2] - ev_off[2 * r + 1] != l))
+            return fail(c, SFGPU_EARG, "bad event array length for contig %d", r);
+        rlens[r] = (int32_t)l;
+    }
+    rc = layout_ref(c, num_ref, rlens.data(), has_reverse != 0);
+    if (rc)
+        return rc;
+    for (int32_t s = 0; s < c->n_seg; s++) {
+        const sf_seg &sg = c->segs[s];
+        cudaError_t e = cudaMemcpy(c->d_stream + sg.off, events + ev_off[s], sizeof(float) * sg.rlen, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            free_ref(c);
+            return fail(c, SFGPU_ECUDA, "cudaMemcpy of reference events: %s", cudaGetErrorString(e));
+        }
+    }
+    c->have_ref = true;
+    return SFGPU_OK;
+}
+
+int sfgpu_submit(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_t *signals,
+                 const int64_t *sig_off, const float *digitisation, const float *offset,
+                 const float *range)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (!c->have_ref)
+        return fail(c, SFGPU_ESTATE, "sfgpu_submit before sfgpu_set_ref");
+    if (slot < 0 || slot >= (int)c->slots.size() || n_reads < 0)
+        return fail(c, SFGPU_EARG, "bad slot or read count");
+    if (n_reads > 0 && (!signals || !sig_off || !digitisation || !offset || !range))
+        return fail(c, SFGPU_EARG, "null batch array");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    // every read starts on a 16-byte boundary so that the event kernel can use 16-byte loads
+    int64_t padded = 0, raw = 0;
+    for (int i = 0; i < n_reads; i++) {
+        const int64_t len = sig_off[i + 1] - sig_off[i];
+        if (len < 0)
+            return fail(c, SFGPU_EARG, "negative signal length for read %d", i);
+        padded += (len + 7) & ~7ll;
+        raw += len;
+    }
+    rc = slot_reserve(c, s, n_reads, padded + 8);
+    if (rc)
+        return rc;
+    int64_t cur = 0;
+    int64_t *h_len = s.h_off + (n_reads + 1);
+    for (int i = 0; i < n_reads; i++) {
+        const int64_t len = sig_off[i + 1] - sig_off[i];
+        s.h_off[i] = cur;
+        h_len[i] = len;
+        memcpy(s.h_signal + cur, signals + sig_off[i], sizeof(int16_t) * (size_t)len);
+        const int64_t end = cur + ((len + 7) & ~7ll);
+        for (int64_t j = cur + len; j < end; j++)
+            s.h_signal[j] = 0;
+        cur = end;
+        s.h_scal[i] = digitisation[i];
+        s.h_scal[s.cap_reads + i] = offset[i];
+        s.h_scal[2 * (size_t)s.cap_reads + i] = range[i];
+    }
+    s.h_off[n_reads] = cur;
+    s.n_reads = n_reads;
+    s.n_samples = cur;
+    s.raw_samples = raw;
+    s.queries_only = false;
+    return run_stages(c, s, true);
+}
+
+int sfgpu_submit_queries(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const float *queries,
+                         const int32_t *qlen)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (!c->have_ref)
+        return fail(c, SFGPU_ESTATE, "sfgpu_submit_queries before a reference was set");
+    if (slot < 0 || slot >= (int)c->slots.size() || n_reads < 0)
+        return fail(c, SFGPU_EARG, "bad slot or read count");
+    if (n_reads > 0 && (!queries || !qlen))
+        return fail(c, SFGPU_EARG, "null batch array");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    rc = slot_reserve(c, s, n_reads, 8);
+    if (rc)
+        return rc;
+    if (!s.h_queries)
+        SF_CUDA(c, cudaMallocHost(&s.h_queries, sizeof(float) * (size_t)s.cap_reads * c->q_cap));
+    const int q = c->opt.query_size;
+    for (int i = 0; i < n_reads; i++) {
+        if (qlen[i] < 0 || qlen[i] > q)
+            return fail(c, SFGPU_EARG, "qlen[%d]=%d outside [0, query_size]", i, qlen[i]);
+        float *dst = s.h_queries + (size_t)i * c->q_cap;
+        memcpy(dst, queries + (size_t)i * q, sizeof(float) * qlen[i]);
+        for (int j = qlen[i]; j < c->q_cap; j++)
+            dst[j] = 0.0f;
+        sf_readinfo ri;
+        memset(&ri, 0, sizeof ri);
+        ri.n_events = qlen[i];
+        ri.qend = qlen[i];
+        ri.qlen = qlen[i];
+        s.h_info[i] = ri;
+    }
+    s.n_reads = n_reads;
+    s.n_samples = 0;
+    s.raw_samples = 0;
+    s.queries_only = true;
+    return run_stages(c, s, true, false);
+}
+
+int sfgpu_resubmit(sfgpu_ctx *c, int32_t slot)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!s.done)
+        return fail(c, SFGPU_ESTATE, "sfgpu_resubmit: slot holds no batch");
+    return run_stages(c, s, false, !s.queries_only);
+}
+
+int sfgpu_collect(sfgpu_ctx *c, int32_t slot, sfgpu_result_t *out)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    if (!s.busy && !s.done)
+        return fail(c, SFGPU_ESTATE, "sfgpu_collect: nothing was submitted to slot %d", slot);
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!out && s.n_reads > 0)
+        return fail(c, SFGPU_EARG, "null result array");
+    for (int i = 0; i < s.n_reads; i++) {
+        const sf_readinfo &ri = s.h_info[i];
+        const sf_hit &h = s.h_hits[i];
+        sfgpu_result_t &o = out[i];
+        o.n_events = ri.n_events;
+        o.qstart = ri.qstart;
+        o.qend = ri.qend;
+        o.qlen = ri.qlen;
+        o.status = ri.status;
+        o.start_raw = ri.start_raw;
+        o.end_raw = ri.end_raw;
+        o.score = h.score;
+        o.score2 = h.score2;
+        o.rid = h.rid;
+        o.strand = h.strand;
+        o.pos_st = h.pos_st;
+        o.pos_end = h.pos_end;
+    }
+    return SFGPU_OK;
+}
+
+int sfgpu_timing(sfgpu_ctx *c, int32_t slot, sfgpu_timing_t *t)
+{
+    if (!c || !t)
+        return fail(c, SFGPU_EARG, "null argument");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!s.done)
+        return fail(c, SFGPU_ESTATE, "sfgpu_timing: slot holds no finished batch");
+    *t = s.timing;
+    return SFGPU_OK;
+}
+
+int sfgpu_ref_events(sfgpu_ctx *c, int32_t rid, int32_t strand, float *out, int32_t cap)
+{
+    if (!c || !c->have_ref)
+        return fail(c, SFGPU_ESTATE, "no reference");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    for (const auto &sg : c->segs) {
+        if (sg.rid == rid && sg.strand == strand) {
+            if (!out || cap < sg.rlen)
+                return fail(c, SFGPU_EARG, "buffer too small (%d < %d)", cap, sg.rlen);
+            SF_CUDA(c, cudaMemcpy(out, c->d_stream + sg.off, sizeof(float) * sg.rlen, cudaMemcpyDeviceToHost));
+            return sg.rlen;
+        }
+    }
+    return fail(c, SFGPU_EARG, "no such (contig, strand)");
+}
+
+int64_t sfgpu_event_table(sfgpu_ctx *c, const int16_t *signal, int64_t n_samples, float digitisation,
+                          float offset, float range, uint64_t *start, float *length, float *mean,
+                          int64_t cap)
+{
+    if (!c || !signal || n_samples <= 0)
+        return fail(c, SFGPU_EARG, "bad argument");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    const int64_t padded = (n_samples + 7) & ~7ll;
+    const int32_t ev_cap = (int32_t)std::min<int64_t>(n_samples + 1, 0x7fffffff);
+    int16_t *d_sig = nullptr;
+    int64_t *d_off = nullptr;
+    float *d_scal = nullptr, *d_mean = nullptr, *d_len = nullptr, *d_q = nullptr;
+    uint64_t *d_start = nullptr;
+    sf_readinfo *d_info = nullptr;
+    sf_readinfo info;
+    memset(&info, 0, sizeof info);
+    int64_t n_ev = 0;
+    int rc = [&]() -> int {
+        SF_CUDA(c, cudaMalloc(&d_sig, sizeof(int16_t) * (padded + 8)));
+        SF_CUDA(c, cudaMemset(d_sig, 0, sizeof(int16_t) * (padded + 8)));
+        SF_CUDA(c, cudaMemcpy(d_sig, signal, sizeof(int16_t) * n_samples, cudaMemcpyHostToDevice));
+        const int64_t offs[3] = {0, padded, n_samples};
+        SF_CUDA(c, cudaMalloc(&d_off, sizeof offs));
+        SF_CUDA(c, cudaMemcpy(d_off, offs, sizeof offs, cudaMemcpyHostToDevice));
+        const float sc[3] = {digitisation, offset, range};
+        SF_CUDA(c, cudaMalloc(&d_scal, sizeof sc));
+        SF_CUDA(c, cudaMemcpy(d_scal, sc, sizeof sc, cudaMemcpyHostToDevice));
+        SF_CUDA(c, cudaMalloc(&d_start, sizeof(uint64_t) * ev_cap));
+        SF_CUDA(c, cudaMalloc(&d_mean, sizeof(float) * ev_cap));
+        SF_CUDA(c, cudaMalloc(&d_len, sizeof(float) * ev_cap));
+        SF_CUDA(c, cudaMalloc(&d_q, sizeof(float) * c->q_cap));
+        SF_CUDA(c, cudaMalloc(&d_info, sizeof(sf_readinfo)));
+        sf_ev_args ea;
+        ea.signal = d_sig;
+        ea.sig_off = d_off;
+        ea.sig_len = d_off + 2;
+        ea.digitisation = d_scal;
+        ea.offset = d_scal + 1;
+        ea.range = d_scal + 2;
+        ea.n_reads = 1;
+        ea.flags = c->opt.flags;
+        ea.q = c->opt.query_size;
+        ea.p = c->opt.prefix_size;
+        ea.ev_cap = ev_cap;
+        ea.ev_start = d_start;
+        ea.ev_mean = d_mean;
+        ea.ev_len = d_len;
+        ea.queries = d_q;
+        ea.q_cap = c->q_cap;
+        ea.info = d_info;
+        ea.keep_all = 1;
+        sf_events_kernel<<<1, SF_EV_THREADS>>>(ea);
+        SF_CUDA(c, cudaGetLastError());
+        SF_CUDA(c, cudaDeviceSynchronize());
+        SF_CUDA(c, cudaMemcpy(&info, d_info, sizeof info, cudaMemcpyDeviceToHost));
+        n_ev = info.n_events;
+        const int64_t m = std::min<int64_t>(n_ev, cap);
+        if (m > 0) {
+            if (start) SF_CUDA(c, cudaMemcpy(start, d_start, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+            if (mean) SF_CUDA(c, cudaMemcpy(mean, d_mean, sizeof(float) * m, cudaMemcpyDeviceToHost));
+            if (length) SF_CUDA(c, cudaMemcpy(length, d_len, sizeof(float) * m, cudaMemcpyDeviceToHost));
+        }
+        return SFGPU_OK;
+    }();
+    dfree(d_sig); dfree(d_off); dfree(d_scal); dfree(d_start); dfree(d_mean); dfree(d_len); dfree(d_q); dfree(d_info);
+    if (rc != SFGPU_OK)
+        return rc;
+    return n_ev;
+}
+
+int sfgpu_query(sfgpu_ctx *c, int32_t slot, int32_t read, float *out, int32_t cap)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!s.done || read < 0 || read >= s.n_reads)
+        return fail(c, SFGPU_EARG, "no such read in slot %d", slot);
+    const int qlen = s.h_info[read].qlen;
+    if (qlen > cap || (qlen > 0 && !out))
+        return fail(c, SFGPU_EARG, "buffer too small");
+    if (qlen > 0)
+        SF_CUDA(c, cudaMemcpy(out, s.d_queries + (size_t)read * c->q_cap, sizeof(float) * qlen, cudaMemcpyDeviceToHost));
+    return qlen;
+}
+
+int64_t sfgpu_ref_columns(const sfgpu_ctx *c) { return c ? c->ref_columns : 0; }
+
+} // extern "C"

@@ -72,6 +72,9 @@ def oracle():
     L.orc_ref_build.argtypes = [C.c_int32, C.POINTER(C.c_char_p), _i32p, _f32p, C.c_int32, C.c_uint32, C.c_int32]
     L.orc_ref_build.restype = C.c_void_p
     L.orc_ref_free.argtypes = [C.c_void_p]
+    L.orc_ref_from_events.argtypes = [C.c_int32, C.c_int32, _i32p, _f32p, C.c_void_p]
+    L.orc_ref_from_events.restype = C.c_void_p
+    L.orc_align_means.argtypes = [C.c_void_p, _f32p, C.c_int32, C.c_uint32, C.POINTER(OrcHit)]
     for fn in ("orc_ref_len", "orc_ref_offset"):
         getattr(L, fn).argtypes = [C.c_void_p, C.c_int32]
         getattr(L, fn).restype = C.c_int32
@@ -137,6 +140,36 @@ class OracleRef:
 
     def rev(self, i):
         return np.ctypeslib.as_array(oracle().orc_ref_rev(self.h, i), shape=(self.length(i),)).copy()
+
+    def close(self):
+        if self.h:
+            oracle().orc_ref_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleEventRef:
+    """oracle reference made of caller-given event arrays (lists of float32 arrays)"""
+
+    def __init__(self, fwd, rev=None):
+        lens = np.array([len(f) for f in fwd], dtype=np.int32)
+        ff = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float32) for f in fwd]))
+        rr = None
+        if rev is not None:
+            rr = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float32) for f in rev]))
+        self.h = oracle().orc_ref_from_events(len(fwd), int(rev is not None), lens, ff,
+                                              rr.ctypes.data_as(C.c_void_p) if rr is not None else None)
+
+    def align(self, means, flags) -> OrcHit:
+        hit = OrcHit()
+        m = np.ascontiguousarray(means, dtype=np.float32)
+        oracle().orc_align_means(self.h, m, m.shape[0], flags, C.byref(hit))
+        return hit
 
     def close(self):
         if self.h:

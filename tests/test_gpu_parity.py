@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libsfgpu.so), against the CPU oracle
+and the golden vectors produced by the unmodified reference.
+
+Bar: bit-exact.  Integer fields (coordinates, strand, contig, window) must be equal; fp32 scores
+are compared by bit pattern (the north star allows 1e-6 relative, we require 0 ulp).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from sigfish_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = json.load(open(os.path.join(H.GOLDEN, "cases.json")))
+_MODELS = {}
+
+
+def model(k):
+    if k not in _MODELS:
+        _MODELS[k] = synth.make_model(k)[0]
+    return _MODELS[k]
+
+
+def bits(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+def assert_hit_equal(g, o, tag, flags, q, p):
+    """g: one row of capi.RESULT_DTYPE, o: helpers.OrcHit"""
+    if not o.mapped:
+        assert g["qlen"] == 0, tag
+        return
+    assert g["qlen"] == o.qend - o.qstart, tag
+    assert (g["qstart"], g["qend"]) == (o.qstart, o.qend), tag
+    assert (g["status"] & 3) == o.status, tag
+    assert (int(g["start_raw"]), int(g["end_raw"])) == (o.start_raw, o.end_raw), tag
+    if flags & H.F_END:
+        assert g["n_events"] == o.n_events, tag
+    else:
+        assert g["n_events"] == min(o.n_events, p + q + 1) or g["n_events"] == o.n_events, tag
+    assert g["rid"] == o.rid, tag
+    assert "+-"[g["strand"]] == o.strand.decode(), tag
+    assert bits(g["score"]) == bits(o.score), (tag, float(g["score"]), o.score)
+    assert bits(g["score2"]) == bits(o.score2), (tag, float(g["score2"]), o.score2)
+    assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
+
+
+# ------------------------------------------------------------------ kernel #2: reference synthesis
+
+REF_COMBOS = sorted({(c["fasta"], c["k"], c["flags"] & ~H.F_DTW, c["q"]) for c in CASES.values()})
+
+
+@pytest.mark.parametrize("fasta,k,flags,q", REF_COMBOS)
+def test_ref_events_bit_exact(fasta, k, flags, q):
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, fasta + ".fa.gz"))
+    ctx = capi.Context(model(k), k, flags=flags, query_size=q)
+    ctx.set_ref(seqs)
+    ref = H.OracleRef(seqs, model(k), k, flags, q)
+    for i in range(len(seqs)):
+        assert ctx.ref_lengths[i] == ref.length(i)
+        assert ctx.ref_st_offset[i] == ref.offset(i)
+        assert ctx.ref_seq_lengths[i] == len(seqs[i])
+        assert np.array_equal(bits(ctx.ref_events(i, 0)), bits(ref.fwd(i))), (fasta, i, "+")
+        if not flags & H.F_RNA:
+            assert np.array_equal(bits(ctx.ref_events(i, 1)), bits(ref.rev(i))), (fasta, i, "-")
+    ref.close()
+    ctx.close()
+
+
+def test_ref_non_acgt_and_lowercase():
+    k = 6
+    rng = np.random.default_rng(5)
+    s = bytearray(synth.random_sequence(3000, rng))
+    for i in rng.integers(0, 3000, size=60):
+        s[i] = ord("N")
+    for i in rng.integers(0, 3000, size=200):
+        s[i] = ord(chr(s[i]).lower())
+    seqs = [bytes(s), synth.random_sequence(k, rng), synth.random_sequence(k + 1, rng)]
+    ctx = capi.Context(model(k), k)
+    ctx.set_ref(seqs)
+    ref = H.OracleRef(seqs, model(k), k, 0, 250)
+    for i in (0, 2):  # a 1-column contig z-scores to NaN on both paths; compare the two others
+        assert np.array_equal(bits(ctx.ref_events(i, 0)), bits(ref.fwd(i)))
+        assert np.array_equal(bits(ctx.ref_events(i, 1)), bits(ref.rev(i)))
+    assert ctx.ref_lengths.tolist() == [2995, 1, 2]
+
+
+# ------------------------------------------------------------------ kernel #1: event detection
+
+@pytest.mark.parametrize("name,rna", [("sp1_dna", False), ("sequin_rna", True), ("synth_dna_short", False)])
+def test_event_tables_match_reference_golden(name, rna):
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, name + ".npz"))
+    z = np.load(os.path.join(H.GOLDEN, f"events_{name}.npz"))
+    offs = z["offsets"]
+    k = 5 if rna else 6
+    ctx = capi.Context(model(k), k, flags=H.F_RNA if rna else 0)
+    for i, (s, c) in enumerate(zip(sigs, sc)):
+        start, length, mean = ctx.event_table(s, c)
+        a, b = offs[i], offs[i + 1]
+        assert len(start) == b - a, (name, i)
+        assert np.array_equal(start, z["start"][a:b]), (name, i)
+        assert np.array_equal(bits(length), bits(z["length"][a:b])), (name, i)
+        assert np.array_equal(bits(mean), bits(z["mean"][a:b])), (name, i)
+    ctx.close()
+
+
+def test_event_tables_random_scalings():
+    """reads whose pA values are not on a coarse grid: prefix sums must still equal the sequential ones"""
+    rng = np.random.default_rng(11)
+    k = 6
+    ctx = capi.Context(model(k), k)
+    for trial in range(6):
+        n = int(rng.integers(400, 9000))
+        lv = rng.uniform(60, 130, size=n // 8 + 2).astype(np.float32)
+        sc = dict(digitisation=float(rng.choice([8192.0, 2048.0, 1000.0])), range=float(rng.uniform(400, 1500)),
+                  offset=float(rng.uniform(-300, 50)), sampling_rate=4000.0)
+        sig = synth.simulate_read(lv, rng, sc)[:n]
+        ev = H.orc_events(sig, sc["digitisation"], sc["offset"], sc["range"], False)
+        start, length, mean = ctx.event_table(sig, sc)
+        assert np.array_equal(start, ev["start"]), trial
+        assert np.array_equal(bits(length), bits(ev["length"])), trial
+        assert np.array_equal(bits(mean), bits(ev["mean"])), trial
+    ctx.close()
+
+
+# ------------------------------------------------------------------ whole path on the golden cases
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_mapping_matches_oracle_on_golden_cases(case):
+    c = CASES[case]
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    k, flags, q, p = c["k"], c["flags"], c["q"], c["p"]
+    ctx = capi.Context(model(k), k, flags=flags, query_size=q, prefix_size=p)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    ref = H.OracleRef(seqs, model(k), k, flags, q)
+    rows = 0
+    for i, (s, cc) in enumerate(zip(sigs, sc)):
+        o = H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], flags, q, p)
+        assert_hit_equal(got[i], o, (case, i), flags, q, p)
+        rows += int(o.mapped)
+    assert rows == c["rows"]
+    ref.close()
+    ctx.close()
+
+
+def test_batch_slots_and_resubmit_are_deterministic():
+    c = CASES["dna_synth48"]
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    ctx = capi.Context(model(c["k"]), c["k"], n_slots=2)
+    ctx.set_ref(seqs)
+    half = len(sigs) // 2
+    ctx.submit(0, *ctx.pack(sigs[:half], sc[:half]))
+    ctx.submit(1, *ctx.pack(sigs[half:], sc[half:]))
+    a = np.concatenate([ctx.collect(0), ctx.collect(1)])
+    b = ctx.map_batch(sigs, sc, slot=0)
+    assert a.tobytes() == b.tobytes()
+    ctx.resubmit(0)
+    assert ctx.collect(0).tobytes() == b.tobytes()
+    t = ctx.timing(0)
+    assert t.dtw_launches == 1 and t.cells > 0 and t.dtw_ms > 0
+    ctx.close()
+
+
+def test_empty_batch_and_empty_read():
+    k = 6
+    rng = np.random.default_rng(2)
+    seqs = [synth.random_sequence(2000, rng)]
+    ctx = capi.Context(model(k), k)
+    ctx.set_ref(seqs)
+    assert len(ctx.map_batch([], [])) == 0
+    sigs, _ = synth.simulate_reads(seqs, k, model(k), 2, seed=3, bases_per_read=400)
+    out = ctx.map_batch([sigs[0], np.zeros(0, np.int16), sigs[1]], [synth.DNA_SCALING] * 3)
+    assert out["qlen"].tolist()[1] == 0 and out["qlen"][0] > 0 and out["qlen"][2] > 0
+    ref = H.OracleRef(seqs, model(k), k, 0, 250)
+    for j, i in ((0, 0), (2, 1)):
+        o = H.orc_map(ref, sigs[i], 8192.0, 10.0, 1402.882, 0, 250, 50)
+        assert_hit_equal(out[j], o, j, 0, 250, 50)
+    ctx.close()
+
+
+# ------------------------------------------------------------------ kernel #3 alone: arbitrary, tie-heavy inputs
+
+def _rand_arrays(rng, lens, quant):
+    out = []
+    for n in lens:
+        y = rng.normal(size=n).astype(np.float32)
+        if quant:
+            y = (np.round(y * quant) / quant).astype(np.float32)
+        out.append(y)
+    return out
+
+
+@pytest.mark.parametrize("q", [20, 33, 64, 100, 250, 300, 500])
+@pytest.mark.parametrize("quant", [0, 2, 1])
+def test_dtw_kernel_matches_oracle_random_and_ties(q, quant):
+    """random and quantised (tie-heavy) queries / references, both strands, ragged query lengths;
+    checkpointing forced on (ck_min_cols) with a tiny restart window so that the start-coordinate pass
+    takes the exit-code path"""
+    rng = np.random.default_rng(1000 * q + quant)
+    lens = [int(x) for x in rng.integers(1, 900, size=5)] + [3000, 1, q, q + 1]
+    fwd = _rand_arrays(rng, lens, quant)
+    rev = _rand_arrays(rng, lens, quant)
+    qlens = [q, q, max(1, q - 1), max(1, q // 2), 25 if q > 25 else q, 1, q, q]
+    queries = _rand_arrays(rng, qlens, quant)
+    oref = H.OracleEventRef(fwd, rev)
+    for ck, win in ((0, 0), (256, 16), (128, 1)):
+        ctx = capi.Context(model(5), 5, query_size=q, ck_min_cols=ck, min_window=win)
+        ctx.set_ref_events(fwd, rev)
+        got = ctx.align_queries(queries)
+        for i, x in enumerate(queries):
+            o = oref.align(x, 0)
+            g = got[i]
+            tag = (q, quant, ck, i)
+            assert g["rid"] == o.rid, tag
+            assert "+-"[g["strand"]] == o.strand.decode(), tag
+            assert bits(g["score"]) == bits(o.score), tag
+            assert bits(g["score2"]) == bits(o.score2), tag
+            assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
+        ctx.close()
+    oref.close()
+
+
+@pytest.mark.parametrize("q", [30, 250, 375])
+@pytest.mark.parametrize("quant", [0, 2])
+def test_std_dtw_kernel_matches_oracle(q, quant):
+    rng = np.random.default_rng(77 * q + quant)
+    lens = [int(x) for x in rng.integers(1, 600, size=40)] + [1, 2, 2000]
+    fwd = _rand_arrays(rng, lens, quant)
+    qlens = [q, q - 1, q // 2, 25, 1, q]
+    queries = _rand_arrays(rng, qlens, quant)
+    oref = H.OracleEventRef(fwd, None)
+    for ck, win in ((0, 0), (128, 1)):
+        ctx = capi.Context(model(5), 5, flags=H.F_RNA | H.F_DTW, query_size=q, ck_min_cols=ck, min_window=win)
+        ctx.set_ref_events(fwd, None)
+        got = ctx.align_queries(queries)
+        for i, x in enumerate(queries):
+            # the ABI takes the query as dtw_single builds it; with RNA and no --invert the oracle
+            # reverses its input, so hand it the reversed array
+            o = oref.align(x[::-1].copy(), H.F_RNA | H.F_DTW)
+            g = got[i]
+            tag = (q, quant, ck, i)
+            assert g["rid"] == o.rid and g["strand"] == 0, tag
+            assert bits(g["score"]) == bits(o.score), tag
+            assert bits(g["score2"]) == bits(o.score2), tag
+            assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
+        ctx.close()
+    oref.close()
+
+
+def test_equal_scores_later_candidate_wins():
+    """identical contigs give identical candidate scores: the later one must be reported"""
+    rng = np.random.default_rng(9)
+    y = rng.normal(size=700).astype(np.float32)
+    x = rng.normal(size=250).astype(np.float32)
+    oref = H.OracleEventRef([y, y, y], [y, y, y])
+    ctx = capi.Context(model(5), 5, query_size=250)
+    ctx.set_ref_events([y, y, y], [y, y, y])
+    g = ctx.align_queries([x])[0]
+    o = oref.align(x, 0)
+    assert (g["rid"], "+-"[g["strand"]]) == (2, "-") == (o.rid, o.strand.decode())
+    assert bits(g["score"]) == bits(g["score2"]) == bits(o.score)
+    assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end)
+    ctx.close()
+
+
+def test_long_reference_round_trip_property():
+    """size-independent property at a length the CPU matrix cannot reach quickly: a query cut out of
+    a 2 M-column reference must come back at its own coordinates with score 0, from either strand"""
+    rng = np.random.default_rng(4)
+    n = 2_000_000
+    y = rng.normal(size=n).astype(np.float32)
+    r = rng.normal(size=n).astype(np.float32)
+    ctx = capi.Context(model(5), 5, query_size=250)
+    ctx.set_ref_events([y], [r])
+    starts = [0, 12345, 999_999, n - 250]
+    queries = [y[s:s + 250] for s in starts] + [r[s:s + 250] for s in starts]
+    got = ctx.align_queries(queries)
+    for i, s in enumerate(starts * 2):
+        g = got[i]
+        assert g["score"] == 0.0 and g["strand"] == i // 4
+        assert (g["pos_st"], g["pos_end"]) == (s, s + 249)
+    ctx.close()
