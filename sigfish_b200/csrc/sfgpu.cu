@@ -743,7 +743,7 @@ int sfgpu_submit(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_t *sig
         padded += (len + 7) & ~7ll;
         raw += len;
     }
-    rc = slot_reserve(c, s, n_reads, padded + 8);
+    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8);
     if (rc)
         return rc;
     int64_t cur = 0;
@@ -785,7 +785,7 @@ int sfgpu_submit_queries(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const floa
     int rc = slot_wait(c, s);
     if (rc)
         return rc;
-    rc = slot_reserve(c, s, n_reads, 8);
+    rc = slot_reserve(c, s, std::max(n_reads, 1), 8);
     if (rc)
         return rc;
     if (!s.h_queries)
