@@ -41,9 +41,12 @@ KMER = 9
 Q, P = 250, 50
 WORKLOAD = "C4: synthetic R10 DNA (k=9), reads x q=250 vs one 1 Mb contig, both strands"
 
-# SASS instructions the DTW inner loop issues per warp for one 32-lane step of R=8 rows
-# (cuobjdump of sf_dtw_score_kernel<8,false>: see profiles/ and DESIGN.md); cells per step = 32*8
-SASS_PER_STEP = 29.0
+# The DTW inner loop issues 28 SASS instructions per warp for one step of 32 lanes x R=8 rows (cuobjdump of
+# sf_dtw_score_kernel<8,false>: 16 FADD + 8 FMNMX3 + LDS + SHFL + IMAD + STS).  FMNMX3 runs on the half-rate
+# ALU pipe and blocks the issue port for 2 cycles (measured: tools/ubench_alu.cu, profiles/r01_ubench_alu.txt),
+# so a step costs 28 + 8 = 36 issue slots.  See DESIGN.md "Roofline".
+SASS_PER_STEP = 28.0
+ISSUE_SLOTS_PER_STEP = 36.0
 ROWS_PER_LANE = 8
 
 
@@ -277,7 +280,8 @@ def main():
         sm_count = torch.cuda.get_device_properties(local).multi_processor_count
         clk = (clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
         # issue-slot roofline of the DTW kernel: one warp instruction per scheduler per cycle
-        peak_cells = sm_count * 4 * clk / SASS_PER_STEP * (32 * ROWS_PER_LANE)
+        peak_cells = sm_count * 4 * clk / ISSUE_SLOTS_PER_STEP * (32 * ROWS_PER_LANE)
+        peak_naive = sm_count * 4 * clk / SASS_PER_STEP * (32 * ROWS_PER_LANE)
         # padded rows are issued but do no algorithmic work: count only qlen of the 32*R rows
         dtw_cells_per_s = cells / (dtw_ms * 1e-3)
         value = job_cells / (ms_step * 1e-3) / 1e9
@@ -299,8 +303,10 @@ def main():
             "roofline": {"bound": "alu-issue", "kernel": "sf_dtw_score_kernel<8,false>",
                          "achieved": dtw_cells_per_s / 1e9, "peak": peak_cells / 1e9, "unit": "GCUPS",
                          "frac": dtw_cells_per_s / peak_cells, "traffic": None,
-                         "peak_source": f"{sm_count} SMs x 4 issue slots x {clk / 1e6:.0f} MHz (median under load) / "
-                                        f"{SASS_PER_STEP:.0f} SASS per 32x{ROWS_PER_LANE} cells",
+                         "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
+                                        f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
+                                        f"({SASS_PER_STEP:.0f} SASS, the 8 half-rate FMNMX3 counted twice)",
+                         "frac_if_every_sass_were_one_slot": dtw_cells_per_s / peak_naive,
                          "events_kernel_GBps": (job_samples / world) * 2 / (evt_ms * 1e-3) / 1e9 if evt_ms > 0 else None,
                          "hbm_peak_GBps": peaks.get("hbm_gbs")},
         }

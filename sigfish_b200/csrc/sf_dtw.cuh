@@ -48,8 +48,94 @@ struct sf_dtw_args {
 
 __host__ __device__ inline int sf_smem_floats_per_warp(int R) { return SF_RING + 32 * R; }
 
+// register of the last query row for which the 32-step block is specialised (the generic block
+// stores all R registers of the last-row lane; the specialised one stores just this one): the
+// common full-length queries of the default -q values (250, 500, 100) and q = multiples of R
+__host__ __device__ constexpr int sf_fast_rq(int R) { return R == 8 ? 1 : (R == 16 ? 3 : (R == 4 ? 3 : R - 1)); }
+
+__host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 8 : (R <= 16 ? 6 : (R <= 24 ? 4 : 3))); }
+
+// Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses whose base is made
+// opaque once per block of 32 steps: otherwise the compiler re-derives the ring / buffer address from
+// its parts on every step (3-4 extra integer instructions per step) to save two registers.
+__device__ __forceinline__ unsigned sf_smem_addr(const void *p)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float sf_lds(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sf_sts(unsigned addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+__device__ __forceinline__ void sf_sts4(unsigned addr, float a, float b, float c, float d)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+
+// 32 wavefront steps.  RQ >= 0: the last query row sits in register RQ of lane lq and only that value
+// is handed to the chunk scan (last[s]); RQ < 0: all R registers are stored (last[s*R + r]).
+template <int R, bool STD, int RQ>
+__device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R], float &bot, float &dprev,
+                                             const float *yb, float *last, const bool is_lq, const int lane,
+                                             const int nz)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned yb_s = sf_smem_addr(yb);
+    const unsigned last_s = sf_smem_addr(last);
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        const float yy = sf_lds(yb_s + 4 * s);
+        float up = __shfl_up_sync(full, bot, 1);
+        if (STD) {
+            if (lane == 0)
+                up = yy == SF_INF ? 0.0f : SF_INF;
+        } else {
+            // lane 0 is fed +0 (virtual row -1); integer multiply keeps this off the half-rate ALU pipe
+            int ub;
+            asm("mul.lo.s32 %0, %1, %2;" : "=r"(ub) : "r"(__float_as_int(up)), "r"(nz)); // IMAD: fma pipe
+            up = __int_as_float(ub);
+        }
+        const float unext = up;
+        float dg = dprev;
+        float t[R];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            t[r] = x[r] - yy;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float m = fminf(fminf(up, dg), L[r]);
+            const float nv = fabsf(t[r]) + m;
+            dg = L[r];
+            L[r] = nv;
+            up = nv;
+        }
+        dprev = unext;
+        bot = L[R - 1];
+        if (is_lq) {
+            if (RQ >= 0) {
+                sf_sts(last_s + 4 * s, L[RQ]);
+            } else if (R % 4 == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r += 4)
+                    sf_sts4(last_s + 4 * (s * R + r), L[r], L[r + 1], L[r + 2], L[r + 3]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    sf_sts(last_s + 4 * (s * R + r), L[r]);
+            }
+        }
+    }
+}
+
 template <int R, bool STD>
-__global__ void __launch_bounds__(SF_DTW_THREADS) sf_dtw_score_kernel(const sf_dtw_args a)
+__global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_score_kernel(const sf_dtw_args a)
 {
     extern __shared__ float sf_smem[];
     const int lane = threadIdx.x & 31;
@@ -81,6 +167,8 @@ __global__ void __launch_bounds__(SF_DTW_THREADS) sf_dtw_score_kernel(const sf_d
         const int lq = (qlen - 1) / R; // lane holding the last query row
         const int rq = (qlen - 1) % R; // its register
         const bool is_lq = lane == lq;
+        const bool fast = rq == sf_fast_rq(R); // warp-uniform
+        const int nz = lane != 0;
 
         // query rows of this lane; rows past qlen are padding (finite, never read back)
         float x[R], L[R];
@@ -126,47 +214,17 @@ __global__ void __launch_bounds__(SF_DTW_THREADS) sf_dtw_score_kernel(const sf_d
             const float ynext = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
             const float *yb = ring + ((b & 1) ? 32 : 64) - lane;
 
-#pragma unroll
-            for (int s = 0; s < 32; s++) {
-                const float yy = yb[s];
-                float up = __shfl_up_sync(full, bot, 1);
-                if (lane == 0)
-                    up = STD ? (yy == SF_INF ? 0.0f : SF_INF) : 0.0f;
-                const float unext = up;
-                float dg = dprev;
-                float t[R];
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    t[r] = x[r] - yy;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const float m = fminf(fminf(up, dg), L[r]);
-                    const float nv = fabsf(t[r]) + m;
-                    dg = L[r];
-                    L[r] = nv;
-                    up = nv;
-                }
-                dprev = unext;
-                bot = L[R - 1];
-                if (is_lq) {
-                    if (R % 4 == 0) {
-#pragma unroll
-                        for (int r = 0; r < R; r += 4)
-                            *reinterpret_cast<float4 *>(last + s * R + r) = make_float4(L[r], L[r + 1], L[r + 2], L[r + 3]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < R; r++)
-                            last[s * R + r] = L[r];
-                    }
-                }
-            }
+            if (fast)
+                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, bot, dprev, yb, last, is_lq, lane, nz);
+            else
+                sf_dtw_block<R, STD, -1>(x, L, bot, dprev, yb, last, is_lq, lane, nz);
             __syncwarp();
 
             // ---- last-row chunk minima (sigfish.c:891-901) ----
             {
                 const int p0 = 32 * b - lq;
                 const int pos = p0 + lane;
-                const float v = last[lane * R + rq];
+                const float v = fast ? last[lane] : last[lane * R + rq];
                 for (;;) {
                     if (pos >= clo && pos < chi && v < rmin) {
                         rmin = v;
