@@ -1,0 +1,266 @@
+/* dtw_cli.c -- `sigfish dtw [OPTIONS] genome.fa reads.blow5` on the B200 path.
+ *
+ * Same options, defaults, validation rules and stderr summary as the reference's dtw_main()
+ * (reference src/dtw_main.c:17-43 option table, 125-285 parsing + validation, 299-326 batch loop,
+ * 331-345 summary).  Differences, all documented in INTEGRATION.md:
+ *   - the batch loop is double buffered: batch n+1 is loaded from disk while batch n is on the GPUs;
+ *   - --gpus N / --gpu-first I choose the devices (default: all visible B200s); reads are sharded
+ *     over them with the reference replicated;
+ *   - --pore rna004 is accepted (the reference's validity test rejects it by mistake);
+ *   - -p < 0 (auto query start, jnn) and --sam are not implemented yet and are refused with a message;
+ *   - --profile-cpu / --accel are accepted and ignored: the stage timers are always printed.
+ */
+#include <errno.h>
+#include <getopt.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sfhost.h"
+
+static struct option long_options[] = {
+    {"slow5", required_argument, 0, 's'},    /* 0 vestigial */
+    {"genome", required_argument, 0, 'g'},   /* 1 vestigial */
+    {"threads", required_argument, 0, 't'},  /* 2 */
+    {"batchsize", required_argument, 0, 'K'}, /* 3 */
+    {"max-bytes", required_argument, 0, 'B'}, /* 4 */
+    {"verbose", required_argument, 0, 'v'},  /* 5 */
+    {"help", no_argument, 0, 'h'},           /* 6 */
+    {"version", no_argument, 0, 'V'},        /* 7 */
+    {"kmer-model", required_argument, 0, 0}, /* 8 */
+    {"meth-model", required_argument, 0, 0}, /* 9 */
+    {"output", required_argument, 0, 'o'},   /* 10 */
+    {"window", required_argument, 0, 'w'},   /* 11 */
+    {"rna", no_argument, 0, 0},              /* 12 */
+    {"prefix", required_argument, 0, 'b'},   /* 13 */
+    {"query-size", required_argument, 0, 'q'}, /* 14 */
+    {"debug-break", required_argument, 0, 0}, /* 15 */
+    {"dtw-std", no_argument, 0, 0},          /* 16 */
+    {"invert", no_argument, 0, 0},           /* 17 */
+    {"secondary", required_argument, 0, 0},  /* 18 */
+    {"full-ref", no_argument, 0, 0},         /* 19 */
+    {"from-end", no_argument, 0, 0},         /* 20 */
+    {"profile-cpu", required_argument, 0, 0}, /* 21 */
+    {"accel", required_argument, 0, 0},      /* 22 */
+    {"sam", no_argument, 0, 'a'},            /* 23 */
+    {"pore", required_argument, 0, 0},       /* 24 */
+    {"gpus", required_argument, 0, 0},       /* 25 B200 */
+    {"gpu-first", required_argument, 0, 0},  /* 26 B200 */
+    {0, 0, 0, 0}};
+
+static int64_t parse_num(const char *str)
+{
+    char *p;
+    double x = strtod(str, &p);
+    if (*p == 'G' || *p == 'g')
+        x *= 1e9;
+    else if (*p == 'M' || *p == 'm')
+        x *= 1e6;
+    else if (*p == 'K' || *p == 'k')
+        x *= 1e3;
+    return (int64_t)(x + .499);
+}
+
+static void yes_or_no(opt_t *opt, uint32_t flag, const char *name, const char *arg)
+{
+    if (!strcmp(arg, "yes") || !strcmp(arg, "y"))
+        opt->flag |= flag;
+    else if (!strcmp(arg, "no") || !strcmp(arg, "n"))
+        opt->flag &= ~flag;
+    else
+        SF_WARNING("option '--%s' only accepts 'yes' or 'no'.", name);
+}
+
+static void print_help_msg(FILE *fp, const opt_t *opt)
+{
+    fprintf(fp, "Usage: sigfish dtw [OPTIONS] genome.fa reads.blow5\n");
+    fprintf(fp, "\nbasic options:\n");
+    fprintf(fp, "   -t INT                     number of host threads decoding records [%d]\n", opt->num_thread);
+    fprintf(fp, "   -K INT                     batch size (max number of reads loaded at once) [%d]\n", opt->batch_size);
+    fprintf(fp, "   -B FLOAT[K/M/G]            max number of bytes loaded at once [%.1fM]\n", opt->batch_size_bytes / (float)(1000 * 1000));
+    fprintf(fp, "   -h                         help\n");
+    fprintf(fp, "   -o FILE                    output to file [stdout]\n");
+    fprintf(fp, "   --verbose INT              verbosity level [%d]\n", (int)opt->verbosity);
+    fprintf(fp, "   --version                  print version\n");
+    fprintf(fp, "   --pore STR                 set the pore chemistry (r9, r10 or rna004) [auto]\n");
+    fprintf(fp, "   --gpus INT                 number of B200 GPUs to shard the reads over [all]\n");
+    fprintf(fp, "   --gpu-first INT            ordinal of the first GPU to use [0]\n");
+    fprintf(fp, "\nadvanced options:\n");
+    fprintf(fp, "   --kmer-model FILE          nucleotide k-mer model file (required: no built-in models in this build)\n");
+    fprintf(fp, "   --rna                      the dataset is direct RNA\n");
+    fprintf(fp, "   -q INT                     the number of events in query signal to align [%d]\n", opt->query_size);
+    fprintf(fp, "   -p INT                     the number of events to trim at query signal start [%d]\n", opt->prefix_size);
+    fprintf(fp, "   --debug-break INT          break after processing the specified no. of batches\n");
+    fprintf(fp, "   --profile-cpu=yes|no       accepted for compatibility (stage timers are always printed)\n");
+    fprintf(fp, "   --dtw-std                  use DTW standard instead of DTW subsequence\n");
+    fprintf(fp, "   --invert                   reverse the reference events instead of query\n");
+    fprintf(fp, "   --full-ref                 map to the full reference\n");
+    fprintf(fp, "   --from-end                 Map the end portion of the query instead of the beginning\n");
+    fprintf(fp, "   --sam                      Output in SAM format (not available yet on the B200 path)\n");
+}
+
+int dtw_main(int argc, char *argv[])
+{
+    const double realtime0 = sf_realtime();
+    const char *optstring = "p:q:t:B:K:v:o:w:ahV";
+    int longindex = 0;
+    int c;
+    FILE *fp_help = stderr;
+    opt_t opt;
+    init_opt(&opt);
+
+    while ((c = getopt_long(argc, argv, optstring, long_options, &longindex)) >= 0) {
+        if (c == 'w') {
+            opt.region_str = optarg;
+        } else if (c == 'B') {
+            opt.batch_size_bytes = parse_num(optarg);
+            if (opt.batch_size_bytes <= 0)
+                SF_FATAL("%s", "Maximum number of bytes should be larger than 0.");
+        } else if (c == 'K') {
+            opt.batch_size = atoi(optarg);
+            if (opt.batch_size < 1)
+                SF_FATAL("Batch size should larger than 0. You entered %d", opt.batch_size);
+        } else if (c == 't') {
+            opt.num_thread = atoi(optarg);
+            if (opt.num_thread < 1)
+                SF_FATAL("Number of threads should larger than 0. You entered %d", opt.num_thread);
+        } else if (c == 'v') {
+            opt.verbosity = (int8_t)atoi(optarg);
+            sf_verbosity = opt.verbosity;
+        } else if (c == 'V') {
+            fprintf(stdout, "sigfish %s\n", SFHOST_VERSION);
+            exit(EXIT_SUCCESS);
+        } else if (c == 'h') {
+            fp_help = stdout;
+        } else if (c == 'p') {
+            opt.prefix_size = atoi(optarg);
+        } else if (c == 'q') {
+            opt.query_size = atoi(optarg);
+            if (opt.query_size < 0)
+                SF_FATAL("Query size should larger than 0. You entered %d", opt.query_size);
+        } else if (c == 0 && longindex == 8) {
+            opt.model_file = optarg;
+        } else if (c == 0 && longindex == 9) {
+            opt.meth_model_file = optarg;
+        } else if (c == 'o') {
+            if (strcmp(optarg, "-") != 0 && freopen(optarg, "wb", stdout) == NULL)
+                SF_FATAL("failed to write the output to file %s : %s", optarg, strerror(errno));
+        } else if (c == 'a') {
+            opt.flag |= SIGFISH_SAM;
+        } else if (c == 0 && longindex == 12) {
+            opt.flag |= SIGFISH_RNA;
+        } else if (c == 0 && longindex == 15) {
+            opt.debug_break = atoi(optarg);
+        } else if (c == 0 && longindex == 16) {
+            opt.flag |= SIGFISH_DTW;
+        } else if (c == 0 && longindex == 17) {
+            opt.flag |= SIGFISH_INV;
+        } else if (c == 0 && longindex == 18) {
+            yes_or_no(&opt, SIGFISH_SEC, "secondary", optarg);
+        } else if (c == 0 && longindex == 19) {
+            opt.flag |= SIGFISH_REF;
+        } else if (c == 0 && longindex == 20) {
+            opt.flag |= SIGFISH_END;
+        } else if (c == 0 && longindex == 21) {
+            yes_or_no(&opt, SIGFISH_PRF, "profile-cpu", optarg);
+        } else if (c == 0 && longindex == 22) {
+            yes_or_no(&opt, SIGFISH_ACC, "accel", optarg);
+        } else if (c == 0 && longindex == 24) {
+            opt.pore = optarg;
+            if (strcmp(opt.pore, "r9") && strcmp(opt.pore, "r10") && strcmp(opt.pore, "rna004"))
+                SF_FATAL("%s", "Pore model should be r9, r10 or rna004");
+            if (!strcmp(opt.pore, "r10")) {
+                opt.flag |= SIGFISH_R10;
+                opt.pore_flag = OPT_PORE_R10;
+            } else if (!strcmp(opt.pore, "rna004")) {
+                opt.flag |= SIGFISH_RNA | SIGFISH_R10;
+                opt.pore_flag = OPT_PORE_RNA004;
+            }
+        } else if (c == 0 && longindex == 25) {
+            opt.num_gpus = atoi(optarg);
+            if (opt.num_gpus < 1)
+                SF_FATAL("Number of GPUs should larger than 0. You entered %d", opt.num_gpus);
+        } else if (c == 0 && longindex == 26) {
+            opt.first_gpu = atoi(optarg);
+        }
+    }
+
+    if (argc - optind != 2 || fp_help == stdout) {
+        print_help_msg(fp_help, &opt);
+        exit(fp_help == stdout ? EXIT_SUCCESS : EXIT_FAILURE);
+    }
+    const char *fastafile = argv[optind];
+    char *slow5file = argv[optind + 1];
+
+    /* src/dtw_main.c:248-277 (the checks run before RNA auto-detection, as in the reference) */
+    if (!(opt.flag & SIGFISH_RNA)) {
+        if (opt.flag & SIGFISH_DTW)
+            SF_FATAL("%s", "DTW is only available for RNA.");
+        if (opt.flag & SIGFISH_INV)
+            SF_FATAL("%s", "Inversion is only available for RNA.");
+        if (opt.flag & SIGFISH_REF)
+            SF_FATAL("%s", "--full-ref is only available for RNA.");
+    }
+    if (opt.prefix_size < 0) {
+        if (!(opt.flag & SIGFISH_RNA))
+            SF_FATAL("%s", "DNA does not support auto query start detection.");
+        if (opt.flag & SIGFISH_INV)
+            SF_FATAL("%s", "Inversion is not compatible with auto query start detection.");
+        if (opt.flag & SIGFISH_END)
+            SF_FATAL("%s", "Mapping from query end is not compatible with auto query start detection.");
+        SF_FATAL("%s", "auto query start detection (-p < 0) is not implemented on the B200 path yet");
+    }
+    if (opt.flag & SIGFISH_SAM)
+        SF_FATAL("%s", "--sam is not implemented on the B200 path yet (PAF only)");
+
+    core_t *core = init_core(fastafile, slow5file, opt, realtime0);
+    /* two batches: one on the GPUs, one being loaded */
+    db_t *db[2] = {init_db(core), init_db(core)};
+    int32_t counter = 0;
+    int cur = 0;
+    ret_status_t status = load_db(core, db[cur]);
+    fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", __func__, sf_realtime() - realtime0,
+            sf_cputime() / (sf_realtime() - realtime0), status.num_reads, status.num_bytes / (1000.0 * 1000.0));
+    for (;;) {
+        const int more = status.num_reads >= core->opt.batch_size || status.num_bytes >= core->opt.batch_size_bytes;
+        const int stop_after = (opt.debug_break == counter);
+        double t0 = sf_realtime();
+        submit_db(core, db[cur]);
+        core->process_db_time += sf_realtime() - t0;
+        ret_status_t next = {0, 0};
+        if (more && !stop_after) { /* overlap: load the next batch while this one is on the GPUs */
+            next = load_db(core, db[cur ^ 1]);
+            fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", __func__, sf_realtime() - realtime0,
+                    sf_cputime() / (sf_realtime() - realtime0), next.num_reads, next.num_bytes / (1000.0 * 1000.0));
+        }
+        t0 = sf_realtime();
+        collect_db(core, db[cur]);
+        core->process_db_time += sf_realtime() - t0;
+        fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) processed\n", __func__, sf_realtime() - realtime0,
+                sf_cputime() / (sf_realtime() - realtime0), status.num_reads, status.num_bytes / (1000.0 * 1000.0));
+        output_db(core, db[cur]);
+        free_db_tmp(db[cur]);
+        if (!more || stop_after)
+            break;
+        counter++;
+        status = next;
+        cur ^= 1;
+    }
+    free_db(db[0]);
+    free_db(db[1]);
+
+    fprintf(stderr, "[%s] total entries: %ld\tprefix fail: %ld\tignored: %ld\ttoo short: %ld", __func__,
+            (long)core->total_reads, (long)core->prefix_fail, (long)core->ignored, (long)core->too_short);
+    fprintf(stderr, "\n[%s] total bytes: %.1f M", __func__, core->sum_bytes / (float)(1000 * 1000));
+    fprintf(stderr, "\n[%s] Data loading time: %.3f sec", __func__, core->load_db_time);
+    fprintf(stderr, "\n[%s] Data processing time: %.3f sec", __func__, core->process_db_time);
+    fprintf(stderr, "\n[%s]     - Parse time (host): %.3f sec", __func__, core->parse_time);
+    fprintf(stderr, "\n[%s]     - H2D time (GPU 0): %.3f sec", __func__, core->h2d_time);
+    fprintf(stderr, "\n[%s]     - Events + normalise time (GPU 0): %.3f sec", __func__, core->event_time);
+    fprintf(stderr, "\n[%s]     - DTW time (GPU 0): %.3f sec", __func__, core->dtw_time);
+    if (core->dtw_time > 0)
+        fprintf(stderr, "\n[%s]     - DTW cells: %.4g on %d GPU(s)", __func__, core->cells, core->num_gpus);
+    fprintf(stderr, "\n[%s] Data output time: %.3f sec", __func__, core->output_time);
+    fprintf(stderr, "\n");
+    free_core(core, opt);
+    return 0;
+}

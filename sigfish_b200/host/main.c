@@ -1,0 +1,41 @@
+/* main.c -- entry of the `sigfish-b200` binary: `sigfish-b200 dtw [OPTIONS] genome.fa reads.blow5`.
+ * Sub-command dispatch and the trailer lines follow reference src/main.c:64-102; only `dtw` exists
+ * here (eval and the other sub-tools are outside the hot path). */
+#include <stdlib.h>
+#include <string.h>
+
+#include "sfhost.h"
+
+static int usage(FILE *fp)
+{
+    fprintf(fp, "Usage: sigfish-b200 <command> [options]\n\n");
+    fprintf(fp, "command:\n");
+    fprintf(fp, "         dtw           map raw signal reads to a reference by subsequence DTW on B200 GPUs\n\n");
+    return fp == stdout ? EXIT_SUCCESS : EXIT_FAILURE;
+}
+
+int main(int argc, char *argv[])
+{
+    const double t0 = sf_realtime();
+    int ret = 1;
+    if (argc < 2)
+        return usage(stderr);
+    if (!strcmp(argv[1], "dtw")) {
+        ret = dtw_main(argc - 1, argv + 1);
+    } else if (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V")) {
+        fprintf(stdout, "sigfish %s\n", SFHOST_VERSION);
+        return EXIT_SUCCESS;
+    } else if (!strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
+        return usage(stdout);
+    } else {
+        fprintf(stderr, "[sigfish-b200] Unrecognised command %s\n", argv[1]);
+        return usage(stderr);
+    }
+    fprintf(stderr, "[%s] Version: %s\n", __func__, SFHOST_VERSION);
+    fprintf(stderr, "[%s] CMD:", __func__);
+    for (int i = 0; i < argc; i++)
+        fprintf(stderr, " %s", argv[i]);
+    fprintf(stderr, "\n[%s] Real time: %.3f sec; CPU time: %.3f sec; Peak RAM: %.3f GB\n\n", __func__,
+            sf_realtime() - t0, sf_cputime(), sf_peakrss() / 1024.0 / 1024.0 / 1024.0);
+    return ret;
+}

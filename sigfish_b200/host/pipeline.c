@@ -1,0 +1,507 @@
+/* pipeline.c -- the batch pipeline of `sigfish dtw` around the B200 C-ABI.
+ *
+ * Mirrors (reference, paths relative to /root/reference):
+ *   init_opt      src/sigfish.c:1122-1144     defaults K=512, B=20 MB, t=8, p=50, q=250
+ *   init_core     src/sigfish.c:81-206        open reads, detect RNA / pore, load model, build reference
+ *   init_db       src/sigfish.c:234-270
+ *   load_db       src/sigfish.c:274-315       up to K records or B bytes of raw records
+ *   process_db    src/sigfish.c:1018-1047     here: decode (host threads) -> pack -> GPUs -> epilogue
+ *   dtw_single    src/sigfish.c:969-985       the part left on the host: strand flip, offset, MAPQ
+ *   aln_to_str    src/sigfish.c:796-826 and paf_str 628-660
+ *   output_db     src/sigfish.c:1051-1086     rows in input order, counters
+ *   free_*        src/sigfish.c:208-231, 1089-1119
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/resource.h>
+#include <sys/time.h>
+
+#include "refio.h"
+#include "s5read.h"
+#include "sfhost.h"
+
+int8_t sf_verbosity = 4;
+
+double sf_realtime(void)
+{
+    struct timeval tp;
+    gettimeofday(&tp, NULL);
+    return tp.tv_sec + tp.tv_usec * 1e-6;
+}
+
+double sf_cputime(void)
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec);
+}
+
+long sf_peakrss(void)
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_maxrss * 1024;
+}
+
+void init_opt(opt_t *opt)
+{
+    memset(opt, 0, sizeof(opt_t));
+    opt->batch_size = 512;
+    opt->batch_size_bytes = 20 * 1000 * 1000;
+    opt->num_thread = 8;
+    opt->debug_break = -1;
+    opt->prefix_size = 50;
+    opt->query_size = 250;
+    opt->verbosity = 4;
+}
+
+/* src/sigfish.c:22-52 */
+static int drna_detect(const sf_s5file_t *sf)
+{
+    const char *exp = sf_s5_hdr_get(sf, "experiment_type", 0);
+    if (!exp) {
+        SF_WARNING("%s", "experiment_type not found in SLOW5 header. Assuming genomic_dna");
+        return 0;
+    }
+    int rna = 0;
+    if (!strcmp(exp, "genomic_dna"))
+        rna = 0;
+    else if (!strcmp(exp, "rna"))
+        rna = 1;
+    else
+        SF_WARNING("Unknown experiment type: %s. Assuming genomic_dna", exp);
+    for (uint32_t g = 1; g < sf_s5_num_read_groups(sf); g++) {
+        const char *cur = sf_s5_hdr_get(sf, "experiment_type", g);
+        if (cur && strcmp(cur, exp))
+            SF_WARNING("Experiment type mismatch: %s != %s in read group %d. Defaulted to %s", cur, exp, (int)g, exp);
+    }
+    return rna;
+}
+
+/* src/sigfish.c:54-80 */
+static int8_t pore_detect(const sf_s5file_t *sf)
+{
+    const char *kit = sf_s5_hdr_get(sf, "sequencing_kit", 0);
+    if (!kit) {
+        SF_WARNING("%s", "sequencing_kit not found in SLOW5 header. Assuming R9.4.1");
+        return OPT_PORE_R9;
+    }
+    int8_t pore = OPT_PORE_R9;
+    if (strstr(kit, "114"))
+        pore = OPT_PORE_R10;
+    else if (strstr(kit, "rna004"))
+        pore = OPT_PORE_RNA004;
+    for (uint32_t g = 1; g < sf_s5_num_read_groups(sf); g++) {
+        const char *cur = sf_s5_hdr_get(sf, "sequencing_kit", g);
+        if (cur && strcmp(cur, kit))
+            SF_WARNING("sequencing_kit type mismatch: %s != %s in read group %d. Defaulted to %s", cur, kit, (int)g, kit);
+    }
+    return pore;
+}
+
+core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double realtime0)
+{
+    core_t *core = (core_t *)calloc(1, sizeof(core_t));
+    char err[512];
+    sf_verbosity = opt.verbosity;
+
+    core->sf = sf_s5_open(slow5file, err, sizeof err);
+    if (!core->sf) {
+        SF_FATAL("Error opening SLOW5 file: %s", err);
+    }
+    if (drna_detect(core->sf)) {
+        opt.flag |= SIGFISH_RNA;
+        if (sf_verbosity >= 3)
+            fprintf(stderr, "[%s] Detected RNA data. --rna was set automatically.\n", __func__);
+    }
+    if (opt.pore == NULL) {
+        const int8_t pore = pore_detect(core->sf);
+        opt.pore_flag = pore;
+        if (pore) {
+            opt.flag |= SIGFISH_R10;
+            if (sf_verbosity >= 3)
+                fprintf(stderr, "[%s] Detected %s data. --pore %s was set automatically.\n", __func__,
+                        pore == OPT_PORE_R10 ? "R10" : "RNA004", pore == OPT_PORE_R10 ? "r10" : "rna004");
+        }
+    }
+
+    /* model (src/sigfish.c:143-164).  The built-in tables of the reference live in src/model.h, which is
+     * not part of the reference mount, so there is nothing to fall back to. */
+    if (!opt.model_file) {
+        SF_FATAL("%s", "no k-mer model: the built-in pore models are not available in this build, pass --kmer-model FILE");
+    }
+    if (sf_model_read(opt.model_file, &core->level_mean, &core->kmer_size, err, sizeof err)) {
+        SF_FATAL("%s", err);
+    }
+
+    /* GPUs */
+    int ndev = sfgpu_device_count();
+    if (ndev < 1) {
+        SF_FATAL("%s", "no sm_100 (B200) GPU visible: this build has no CPU path");
+    }
+    int first = opt.first_gpu > 0 ? opt.first_gpu : 0;
+    int want = opt.num_gpus > 0 ? opt.num_gpus : ndev - first;
+    if (first + want > ndev || want < 1) {
+        SF_FATAL("requested GPUs %d..%d but %d visible", first, first + want - 1, ndev);
+    }
+    if (want > SFHOST_MAX_GPUS)
+        want = SFHOST_MAX_GPUS;
+    core->num_gpus = want;
+
+    /* reference (replaces gen_ref, src/sigfish.c:178): FASTA on the host, events on every GPU */
+    sf_fasta_t fa;
+    if (sf_fasta_read(fastafile, &fa, err, sizeof err)) {
+        SF_FATAL("%s", err);
+    }
+    refsynth_t *ref = (refsynth_t *)calloc(1, sizeof(refsynth_t));
+    ref->num_ref = fa.num_ref;
+    ref->ref_names = fa.names;
+    ref->ref_lengths = (int32_t *)calloc(fa.num_ref, sizeof(int32_t));
+    ref->ref_seq_lengths = (int32_t *)calloc(fa.num_ref, sizeof(int32_t));
+    ref->ref_st_offset = (int32_t *)calloc(fa.num_ref, sizeof(int32_t));
+    core->ref = ref;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < fa.off[fa.num_ref]; i++) {
+        switch (fa.bases[i]) {
+        case 'A': case 'C': case 'G': case 'T': case 'a': case 'c': case 'g': case 't': break;
+        default: bad++;
+        }
+    }
+    if (bad)
+        SF_WARNING("%ld non-ACGT reference bases are treated as 'A' (reverse strand: 'T'), as in the reference", (long)bad);
+
+    for (int g = 0; g < core->num_gpus; g++) {
+        sfgpu_opt_t go;
+        memset(&go, 0, sizeof go);
+        go.device = first + g;
+        go.flags = opt.flag & (SFGPU_RNA | SFGPU_DTW | SFGPU_INV | SFGPU_REF | SFGPU_END | SFGPU_SAM);
+        go.query_size = opt.query_size;
+        go.prefix_size = opt.prefix_size;
+        go.kmer_size = (int32_t)core->kmer_size;
+        go.n_slots = 2;
+        if (sfgpu_create(&core->gpu[g], &go, core->level_mean) != SFGPU_OK) {
+            SF_FATAL("GPU %d: %s", first + g, sfgpu_strerror(NULL));
+        }
+        if (sfgpu_set_ref(core->gpu[g], fa.num_ref, fa.bases, fa.off, ref->ref_lengths, ref->ref_seq_lengths,
+                          ref->ref_st_offset) != SFGPU_OK) {
+            SF_FATAL("GPU %d: %s", first + g, sfgpu_strerror(core->gpu[g]));
+        }
+    }
+    free(fa.bases);
+    free(fa.off);
+
+    core->opt = opt;
+    core->realtime0 = realtime0;
+    return core;
+}
+
+void free_core(core_t *core, opt_t opt)
+{
+    (void)opt;
+    for (int g = 0; g < core->num_gpus; g++)
+        sfgpu_destroy(core->gpu[g]);
+    if (core->ref) {
+        for (int i = 0; i < core->ref->num_ref; i++)
+            free(core->ref->ref_names[i]);
+        free(core->ref->ref_names);
+        free(core->ref->ref_lengths);
+        free(core->ref->ref_seq_lengths);
+        free(core->ref->ref_st_offset);
+        free(core->ref);
+    }
+    free(core->level_mean);
+    sf_s5_close(core->sf);
+    free(core);
+}
+
+db_t *init_db(core_t *core)
+{
+    db_t *db = (db_t *)calloc(1, sizeof(db_t));
+    const size_t n = (size_t)core->opt.batch_size;
+    db->capacity_rec = core->opt.batch_size;
+    db->mem_records = (char **)calloc(n, sizeof(char *));
+    db->mem_bytes = (size_t *)calloc(n, sizeof(size_t));
+    db->mem_cap = (size_t *)calloc(n, sizeof(size_t));
+    db->rec = (sf_rec_t *)calloc(n, sizeof(sf_rec_t));
+    db->res = (sfgpu_result_t *)calloc(n, sizeof(sfgpu_result_t));
+    db->aln = (aln_t *)calloc(n, sizeof(aln_t));
+    db->out = (char **)calloc(n, sizeof(char *));
+    db->sig_off = (int64_t *)calloc(n + 1, sizeof(int64_t));
+    db->dig = (float *)calloc(n, sizeof(float));
+    db->off = (float *)calloc(n, sizeof(float));
+    db->rng = (float *)calloc(n, sizeof(float));
+    return db;
+}
+
+ret_status_t load_db(core_t *core, db_t *db)
+{
+    const double t0 = sf_realtime();
+    db->n_rec = 0;
+    db->sum_bytes = 0;
+    db->total_reads = 0;
+    db->prefix_fail = 0;
+    db->ignored = 0;
+    db->too_short = 0;
+    db->submitted = 0;
+    ret_status_t status = {0, 0};
+    while (db->n_rec < db->capacity_rec && db->sum_bytes < core->opt.batch_size_bytes) {
+        const int i = db->n_rec;
+        const int64_t got = sf_s5_get_next_mem(core->sf, &db->mem_records[i], &db->mem_cap[i]);
+        if (got < 0) {
+            SF_FATAL("Error reading from SLOW5 file: %s", sf_s5_error(core->sf));
+        }
+        if (got == 0)
+            break;
+        db->mem_bytes[i] = (size_t)got;
+        db->n_rec++;
+        db->total_reads++;
+        db->sum_bytes += got;
+    }
+    status.num_reads = db->n_rec;
+    status.num_bytes = db->sum_bytes;
+    core->load_db_time += sf_realtime() - t0;
+    return status;
+}
+
+/* ---- record decoding on host threads (parse_single, src/sigfish.c:317-328) ---- */
+typedef struct {
+    core_t *core;
+    db_t *db;
+    int32_t *next;
+    char *scratch;
+    size_t scratch_cap;
+    int failed;
+} parse_arg_t;
+
+static void *parse_worker(void *p)
+{
+    parse_arg_t *a = (parse_arg_t *)p;
+    for (;;) {
+        const int32_t i = __sync_fetch_and_add(a->next, 1);
+        if (i >= a->db->n_rec)
+            break;
+        if (sf_s5_parse(a->core->sf, a->db->mem_records[i], a->db->mem_bytes[i], &a->db->rec[i], &a->scratch,
+                        &a->scratch_cap)) {
+            a->failed = i + 1;
+            break;
+        }
+    }
+    free(a->scratch);
+    a->scratch = NULL;
+    return NULL;
+}
+
+static void parse_db(core_t *core, db_t *db)
+{
+    int nt = core->opt.num_thread < 1 ? 1 : core->opt.num_thread;
+    if (nt > db->n_rec)
+        nt = db->n_rec > 0 ? db->n_rec : 1;
+    int32_t next = 0;
+    parse_arg_t *args = (parse_arg_t *)calloc((size_t)nt, sizeof(parse_arg_t));
+    pthread_t *tid = (pthread_t *)calloc((size_t)nt, sizeof(pthread_t));
+    for (int t = 0; t < nt; t++) {
+        args[t].core = core;
+        args[t].db = db;
+        args[t].next = &next;
+    }
+    if (nt == 1) {
+        parse_worker(&args[0]);
+    } else {
+        for (int t = 0; t < nt; t++)
+            if (pthread_create(&tid[t], NULL, parse_worker, &args[t])) {
+                SF_FATAL("%s", "pthread_create failed");
+            }
+        for (int t = 0; t < nt; t++)
+            pthread_join(tid[t], NULL);
+    }
+    for (int t = 0; t < nt; t++)
+        if (args[t].failed) {
+            SF_FATAL("Error parsing the record %d of the batch", args[t].failed - 1);
+        }
+    free(args);
+    free(tid);
+}
+
+void submit_db(core_t *core, db_t *db)
+{
+    const double t0 = sf_realtime();
+    parse_db(core, db);
+    core->parse_time += sf_realtime() - t0;
+
+    /* shards: contiguous read ranges with about the same number of samples each */
+    const int G = core->num_gpus;
+    int64_t total = 0;
+    for (int i = 0; i < db->n_rec; i++)
+        total += (int64_t)db->rec[i].len_raw_signal;
+    int64_t acc = 0;
+    int g = 0;
+    db->shard_begin[0] = 0;
+    for (int i = 0; i < db->n_rec && g + 1 < G; i++) {
+        acc += (int64_t)db->rec[i].len_raw_signal;
+        if (acc * G >= total * (g + 1)) {
+            g++;
+            db->shard_begin[g] = i + 1;
+        }
+    }
+    while (g < G) {
+        g++;
+        db->shard_begin[g] = db->n_rec;
+    }
+
+    db->slot = core->next_slot;
+    core->next_slot ^= 1;
+    for (g = 0; g < G; g++) {
+        const int b = db->shard_begin[g], e = db->shard_begin[g + 1];
+        /* gather the shard's signals into one host buffer; the library copies it into pinned staging */
+        int64_t n = 0;
+        for (int i = b; i < e; i++)
+            n += (int64_t)db->rec[i].len_raw_signal;
+        int16_t *flat = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n > 0 ? n : 1));
+        int64_t cur = 0;
+        for (int i = b; i < e; i++) {
+            const sf_rec_t *r = &db->rec[i];
+            db->sig_off[i - b] = cur;
+            memcpy(flat + cur, r->raw_signal, sizeof(int16_t) * (size_t)r->len_raw_signal);
+            cur += (int64_t)r->len_raw_signal;
+            /* narrowed to float exactly as event_single() does (src/sigfish.c:335-337) */
+            db->dig[i - b] = (float)r->digitisation;
+            db->off[i - b] = (float)r->offset;
+            db->rng[i - b] = (float)r->range;
+        }
+        db->sig_off[e - b] = cur;
+        if (sfgpu_submit(core->gpu[g], db->slot, e - b, flat, db->sig_off, db->dig, db->off, db->rng) != SFGPU_OK) {
+            SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
+        }
+        free(flat);
+    }
+    db->submitted = 1;
+}
+
+/* (int)round(x) as the x86-64 reference evaluates it (cvttsd2si: out of range -> INT_MIN) */
+static int32_t to_int_like_x86(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        return (int32_t)0x80000000;
+    return (int32_t)v;
+}
+
+static char *paf_str(const aln_t *aln, const char *read_id, const char *rname, uint64_t start_raw, uint64_t end_raw,
+                     uint64_t query_size, uint64_t len_raw_signal, uint64_t rlength)
+{
+    /* src/sigfish.c:628-660 */
+    const float block_len = (float)(aln->pos_end - aln->pos_st);
+    const float residue = block_len - aln->score * block_len / (float)query_size;
+    const size_t cap = strlen(read_id) + strlen(rname) + 256;
+    char *s = (char *)malloc(cap);
+    snprintf(s, cap, "%s\t%ld\t%ld\t%ld\t%c\t%s\t%d\t%d\t%d\t%d\t%d\t%d\ttp:A:P\td1:f:%.2f\td2:f:%.2f\n", read_id,
+             (long)len_raw_signal, (long)start_raw, (long)end_raw, aln->d, rname, (int)rlength, aln->pos_st, aln->pos_end,
+             to_int_like_x86(round((double)residue)), to_int_like_x86(round((double)block_len)), aln->mapq,
+             (double)aln->score, (double)aln->score2);
+    return s;
+}
+
+void collect_db(core_t *core, db_t *db)
+{
+    if (!db->submitted)
+        return;
+    for (int g = 0; g < core->num_gpus; g++) {
+        const int b = db->shard_begin[g];
+        if (sfgpu_collect(core->gpu[g], db->slot, db->res + b) != SFGPU_OK) {
+            SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
+        }
+        sfgpu_timing_t t;
+        if (sfgpu_timing(core->gpu[g], db->slot, &t) == SFGPU_OK) {
+            if (g == 0) {
+                core->h2d_time += t.h2d_ms * 1e-3;
+                core->event_time += t.events_ms * 1e-3;
+                core->dtw_time += (t.dtw_ms + t.trace_ms) * 1e-3;
+                core->d2h_time += t.d2h_ms * 1e-3;
+            }
+            core->cells += t.cells;
+        }
+    }
+    db->submitted = 0;
+    const refsynth_t *ref = core->ref;
+    for (int i = 0; i < db->n_rec; i++) {
+        const sfgpu_result_t *r = &db->res[i];
+        db->out[i] = NULL;
+        if (r->status & 1)
+            db->ignored++;
+        if (r->status & 2)
+            db->too_short++;
+        if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0)
+            continue;
+        /* src/sigfish.c:969-985 */
+        aln_t *a = &db->aln[i];
+        a->score = r->score;
+        a->score2 = r->score2;
+        a->rid = r->rid;
+        a->d = r->strand ? '-' : '+';
+        const int32_t rlen = ref->ref_lengths[r->rid];
+        a->pos_st = r->strand ? rlen - r->pos_end : r->pos_st;
+        a->pos_end = r->strand ? rlen - r->pos_st : r->pos_end;
+        a->pos_st += ref->ref_st_offset[r->rid];
+        a->pos_end += ref->ref_st_offset[r->rid];
+        const float ratio = 500 * (a->score2 - a->score) / a->score;
+        int32_t mq = to_int_like_x86(round((double)ratio));
+        if (mq > 60)
+            mq = 60;
+        a->mapq = (uint8_t)mq;
+        /* src/sigfish.c:800-807: query_size = (qend-1) - qstart */
+        const uint64_t query_size = (uint64_t)(r->qend - 1) - (uint64_t)r->qstart;
+        db->out[i] = paf_str(a, db->rec[i].read_id, ref->ref_names[r->rid], r->start_raw, r->end_raw, query_size,
+                             db->rec[i].len_raw_signal, (uint64_t)ref->ref_seq_lengths[r->rid]);
+    }
+}
+
+void process_db(core_t *core, db_t *db)
+{
+    const double t0 = sf_realtime();
+    submit_db(core, db);
+    collect_db(core, db);
+    core->process_db_time += sf_realtime() - t0;
+}
+
+void output_db(core_t *core, db_t *db)
+{
+    const double t0 = sf_realtime();
+    for (int i = 0; i < db->n_rec; i++)
+        if (db->out[i])
+            fputs(db->out[i], stdout);
+    fflush(stdout);
+    core->sum_bytes += db->sum_bytes;
+    core->total_reads += db->total_reads;
+    core->prefix_fail += db->prefix_fail;
+    core->ignored += db->ignored;
+    core->too_short += db->too_short;
+    core->output_time += sf_realtime() - t0;
+}
+
+void free_db_tmp(db_t *db)
+{
+    for (int i = 0; i < db->n_rec; i++) {
+        free(db->out[i]);
+        db->out[i] = NULL;
+    }
+}
+
+void free_db(db_t *db)
+{
+    for (int i = 0; i < db->capacity_rec; i++) {
+        free(db->mem_records[i]);
+        free(db->rec[i].read_id);
+        free(db->rec[i].raw_signal);
+    }
+    free(db->mem_records); free(db->mem_bytes); free(db->mem_cap); free(db->rec); free(db->res); free(db->aln);
+    free(db->out); free(db->sig_off); free(db->dig); free(db->off); free(db->rng);
+    free(db);
+}
+
+void sam_hdr_wr(const refsynth_t *ref)
+{
+    /* src/dtw_main.c:118-123: LN is the k-mer count, as in the reference */
+    for (int i = 0; i < ref->num_ref; i++)
+        printf("@SQ\tSN:%s\tLN:%d\n", ref->ref_names[i], ref->ref_lengths[i]);
+}

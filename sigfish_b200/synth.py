@@ -155,3 +155,53 @@ def tmpdir() -> str:
     d = os.environ.get("SIGFISH_B200_TMP", "/tmp/sigfish_b200")
     os.makedirs(d, exist_ok=True)
     return d
+
+
+# ---------------------------------------------------------------- BLOW5 writer (test inputs)
+
+def _svb_zd_encode(sig: np.ndarray) -> bytes:
+    """StreamVByte(zigzag(delta)) of an int16 signal, the BLOW5 'svb-zd' signal codec:
+    u32 count, ceil(count/4) key bytes (2 bits per value: byte length - 1), then the data bytes."""
+    x = sig.astype(np.int64)
+    d = np.diff(x, prepend=0)
+    z = ((d << 1) ^ (d >> 63)).astype(np.uint32)
+    nbytes = np.where(z < (1 << 8), 1, np.where(z < (1 << 16), 2, np.where(z < (1 << 24), 3, 4))).astype(np.uint8)
+    n = z.shape[0]
+    codes = np.zeros(((n + 3) // 4) * 4, dtype=np.uint8)
+    codes[:n] = nbytes - 1
+    c4 = codes.reshape(-1, 4)
+    keys = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+    raw = z.view(np.uint8).reshape(-1, 4)  # little endian
+    mask = np.arange(4)[None, :] < nbytes[:, None]
+    data = raw[mask]
+    return np.uint32(n).tobytes() + keys.tobytes() + data.tobytes()
+
+
+def write_blow5(path: str, read_ids, signals, rna: bool = False, kit: str | None = None,
+                scaling: dict | None = None, scalings=None, record_zlib: bool = True, signal_svb: bool = True) -> None:
+    """BLOW5 v0.2.0 file (zlib records, svb-zd signal by default) with the primary fields only."""
+    import struct
+    import zlib
+    scaling = scaling or (RNA_SCALING if rna else DNA_SCALING)
+    kit = kit or ("sqk-rna002" if rna else "sqk-lsk109")
+    hdr = (f"#slow5_version\t0.2.0\n#num_read_groups\t1\n@experiment_type\t{'rna' if rna else 'genomic_dna'}\n"
+           f"@sequencing_kit\t{kit}\n#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n"
+           "#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n").encode()
+    with open(path, "wb") as f:
+        head = b"BLOW5\x01" + bytes([0, 2, 0]) + bytes([1 if record_zlib else 0]) + struct.pack("<I", 1) + \
+            bytes([1 if signal_svb else 0])
+        f.write(head + b"\x00" * (64 - len(head)))
+        f.write(struct.pack("<I", len(hdr)) + hdr)
+        for i, (rid, sig) in enumerate(zip(read_ids, signals)):
+            sc = scalings[i] if scalings is not None else scaling
+            sig = np.ascontiguousarray(sig, dtype=np.int16)
+            body = sig.tobytes() if not signal_svb else _svb_zd_encode(sig)
+            n_field = len(sig) if not signal_svb else len(body)
+            rid_b = rid.encode()
+            rec = struct.pack("<H", len(rid_b)) + rid_b + struct.pack("<I", 0) + \
+                struct.pack("<dddd", sc["digitisation"], sc["offset"], sc["range"], sc["sampling_rate"]) + \
+                struct.pack("<Q", n_field) + body
+            if record_zlib:
+                rec = zlib.compress(rec)
+            f.write(struct.pack("<Q", len(rec)) + rec)
+        f.write(b"5WOLB")

@@ -1,0 +1,100 @@
+"""End-to-end drop-in test on the GPU: `sigfish-b200 dtw` (C host + libsfgpu) must print, byte for byte,
+the PAF the unmodified reference binary printed for the same inputs (tests/golden/paf/*.paf)."""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from sigfish_b200 import build as B
+from sigfish_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = json.load(open(os.path.join(H.GOLDEN, "cases.json")))
+
+
+@pytest.fixture(scope="module")
+def cli():
+    B.build_all()
+    assert os.path.exists(B.CLI)
+    return B.CLI
+
+
+def _inputs(tmp, case, fmt):
+    c = CASES[case]
+    fa = os.path.join(tmp, "ref.fa")
+    with gzip.open(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    rna = bool(c["flags"] & H.F_RNA)
+    kit = "sqk-lsk114" if c["k"] == 9 else None
+    reads = os.path.join(tmp, "reads." + fmt)
+    if fmt == "slow5":
+        synth.write_slow5_ascii(reads, ids, sigs, rna=rna, kit=kit, scalings=sc)
+    else:
+        synth.write_blow5(reads, ids, sigs, rna=rna, kit=kit, scalings=sc)
+    mean, stdv = synth.make_model(c["k"])
+    mf = os.path.join(tmp, "model.txt")
+    synth.write_model_file(mf, c["k"], mean, stdv)
+    return c, fa, reads, mf
+
+
+def _run(cli, c, fa, reads, mf, extra=()):
+    cmd = [cli, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"])] + H.flags_to_cli(c["flags"]) + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout, r.stderr
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_cli_paf_is_byte_identical_to_reference(cli, tmp_path, case):
+    fmt = "blow5" if sum(map(ord, case)) % 2 else "slow5"
+    c, fa, reads, mf = _inputs(str(tmp_path), case, fmt)
+    out, err = _run(cli, c, fa, reads, mf)
+    want = open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read()
+    assert out == want
+    assert "total entries" in err and "DTW time" in err
+
+
+@pytest.mark.parametrize("case,extra", [("dna_synth48", ["-K", "7", "-t", "3"]), ("dna_synth48", ["-B", "30K"]),
+                                        ("rna_synth32", ["-K", "32"]), ("dna_multi_contig", ["-K", "1"]),
+                                        ("dna_synth48", ["--debug-break", "1", "-K", "10"])])
+def test_cli_batching_does_not_change_output(cli, tmp_path, case, extra):
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, _ = _run(cli, c, fa, reads, mf, extra)
+    want = open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read()
+    if "--debug-break" in extra:  # stops after N+1 batches (dtw_main.c:322-325)
+        want = "".join(want.splitlines(keepends=True)[:20])
+    assert out == want
+
+
+def test_cli_read_sharding_over_gpus(cli, tmp_path):
+    n = capi.lib().sfgpu_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_synth48", "blow5")
+    want = open(os.path.join(H.GOLDEN, "paf", "dna_synth48.paf")).read()
+    for g in sorted({2, n}):
+        out, err = _run(cli, c, fa, reads, mf, ["--gpus", str(g), "-K", "20"])
+        assert out == want
+        assert f"on {g} GPU(s)" in err
+
+
+def test_cli_errors_like_the_reference(cli, tmp_path):
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "slow5")
+    for extra, msg in ((["--dtw-std"], "DTW is only available for RNA"), (["--invert"], "Inversion is only available for RNA"),
+                       (["--full-ref"], "--full-ref is only available for RNA"), (["-p", "-1"], "DNA does not support auto query start"),
+                       (["--pore", "r11"], "Pore model should be")):
+        r = subprocess.run([cli, "dtw", fa, reads, "--kmer-model", mf] + extra, capture_output=True, text=True)
+        assert r.returncode != 0 and msg in r.stderr, (extra, r.stderr)
+    r = subprocess.run([cli, "dtw", fa, reads], capture_output=True, text=True)
+    assert r.returncode != 0 and "--kmer-model" in r.stderr
+    r = subprocess.run([cli, "dtw", fa], capture_output=True, text=True)
+    assert r.returncode != 0 and "Usage: sigfish dtw" in r.stderr
+    r = subprocess.run([cli, "dtw", fa, str(tmp_path / "missing.blow5"), "--kmer-model", mf], capture_output=True, text=True)
+    assert r.returncode != 0 and "Error opening SLOW5 file" in r.stderr

@@ -1,0 +1,149 @@
+"""CPU tests of the host-side readers (sigfish_b200/host): SLOW5 / BLOW5 records, FASTA, k-mer model.
+They run without a GPU: libsfhost.so only needs libsfgpu.so to load."""
+import ctypes as C
+import gzip
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import helpers as H
+from sigfish_b200 import build as B
+from sigfish_b200 import synth
+
+
+class SfRec(C.Structure):
+    _fields_ = [("read_id", C.c_char_p), ("digitisation", C.c_double), ("offset", C.c_double), ("range", C.c_double),
+                ("sampling_rate", C.c_double), ("len_raw_signal", C.c_uint64), ("raw_signal", C.POINTER(C.c_int16)),
+                ("cap_signal", C.c_size_t)]
+
+
+class SfFasta(C.Structure):
+    _fields_ = [("num_ref", C.c_int32), ("names", C.POINTER(C.c_char_p)), ("bases", C.POINTER(C.c_char)),
+                ("off", C.POINTER(C.c_int64))]
+
+
+@pytest.fixture(scope="module")
+def host():
+    B.build_all()
+    L = C.CDLL(B.LIB_HOST)
+    L.sf_s5_open.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.sf_s5_open.restype = C.c_void_p
+    L.sf_s5_close.argtypes = [C.c_void_p]
+    L.sf_s5_hdr_get.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+    L.sf_s5_hdr_get.restype = C.c_char_p
+    L.sf_s5_get_next_mem.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.sf_s5_get_next_mem.restype = C.c_int64
+    L.sf_s5_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(SfRec), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.sf_fasta_read.argtypes = [C.c_char_p, C.POINTER(SfFasta), C.c_char_p, C.c_size_t]
+    L.sf_model_read.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]
+    return L
+
+
+def read_all(L, path):
+    err = C.create_string_buffer(512)
+    f = L.sf_s5_open(path.encode(), err, 512)
+    assert f, err.value
+    out = []
+    mem, cap = C.c_void_p(), C.c_size_t(0)
+    scratch, scap = C.c_void_p(), C.c_size_t(0)
+    rec = SfRec()
+    total = 0
+    while True:
+        n = L.sf_s5_get_next_mem(f, C.byref(mem), C.byref(cap))
+        assert n >= 0
+        if n == 0:
+            break
+        total += n
+        assert L.sf_s5_parse(f, mem, n, C.byref(rec), C.byref(scratch), C.byref(scap)) == 0
+        sig = np.ctypeslib.as_array(rec.raw_signal, shape=(rec.len_raw_signal,)).copy() if rec.len_raw_signal else np.zeros(0, np.int16)
+        out.append((rec.read_id.decode(), rec.digitisation, rec.offset, rec.range, rec.sampling_rate, sig))
+    kit = L.sf_s5_hdr_get(f, b"sequencing_kit", 0)
+    exp = L.sf_s5_hdr_get(f, b"experiment_type", 0)
+    assert L.sf_s5_hdr_get(f, b"no_such_attribute", 0) is None
+    L.sf_s5_close(f)
+    return out, kit, exp, total
+
+
+@pytest.mark.parametrize("fmt", ["slow5", "blow5_zlib_svb", "blow5_zlib_raw", "blow5_none_svb", "blow5_none_raw"])
+@pytest.mark.parametrize("name,rna", [("sp1_dna", False), ("sequin_rna", True)])
+def test_slow5_blow5_round_trip(host, tmp_path, fmt, name, rna):
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, name + ".npz"))
+    sigs = list(sigs) + [np.zeros(0, np.int16), np.array([-32768, 32767, 0, -1, 1], np.int16)]
+    ids = ids + ["empty", "extremes"]
+    sc = sc + [sc[0], sc[0]]
+    p = str(tmp_path / ("r." + ("slow5" if fmt == "slow5" else "blow5")))
+    if fmt == "slow5":
+        synth.write_slow5_ascii(p, ids, sigs, rna=rna, scalings=sc)
+    else:
+        synth.write_blow5(p, ids, sigs, rna=rna, scalings=sc, record_zlib="zlib" in fmt, signal_svb="svb" in fmt)
+    got, kit, exp, total = read_all(host, p)
+    assert exp == (b"rna" if rna else b"genomic_dna") and kit is not None
+    assert [g[0] for g in got] == ids
+    for g, s, c in zip(got, sigs, sc):
+        assert (g[1], g[2], g[3], g[4]) == (c["digitisation"], c["offset"], c["range"], c["sampling_rate"])
+        assert np.array_equal(g[5], s)
+    assert total > 0
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("name", ["sp1_dna", "sequin_rna"])
+def test_reads_bundled_reference_blow5(host, name):
+    """the reference's own BLOW5 test files (zlib records, svb-zd signal, auxiliary fields), decoded by
+    our reader, against the signals slow5lib decoded (tests/golden/*.npz).  Build container only."""
+    p = f"/root/reference/test/{name}.blow5"
+    if not os.path.exists(p):
+        pytest.skip("reference mount not present")
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, name + ".npz"))
+    got, kit, exp, _ = read_all(host, p)
+    assert [g[0] for g in got] == ids
+    for g, s, c in zip(got, sigs, sc):
+        assert (g[1], g[2], g[3]) == (c["digitisation"], c["offset"], c["range"])
+        assert np.array_equal(g[5], s)
+
+
+def test_fasta_reader_plain_and_gzip(host, tmp_path):
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, "synth_multi.fa.gz"))
+    plain = str(tmp_path / "m.fa")
+    with gzip.open(os.path.join(H.GOLDEN, "synth_multi.fa.gz"), "rb") as fi, open(plain, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    for p in (plain, os.path.join(H.GOLDEN, "synth_multi.fa.gz")):
+        fa = SfFasta()
+        err = C.create_string_buffer(512)
+        assert host.sf_fasta_read(p.encode(), C.byref(fa), err, 512) == 0, err.value
+        assert fa.num_ref == len(names)
+        for i in range(fa.num_ref):
+            assert fa.names[i].decode() == names[i]
+            assert C.string_at(C.addressof(fa.bases.contents) + fa.off[i], fa.off[i + 1] - fa.off[i]) == seqs[i]
+    # header with a description, Windows line ends, blank lines
+    odd = str(tmp_path / "odd.fa")
+    open(odd, "wb").write(b">c1 some description\r\nACGT\r\n\r\nacgtn\r\n>c2\tx\nTT\n")
+    fa = SfFasta()
+    err = C.create_string_buffer(512)
+    assert host.sf_fasta_read(odd.encode(), C.byref(fa), err, 512) == 0
+    assert [fa.names[i] for i in range(2)] == [b"c1", b"c2"]
+    assert C.string_at(C.addressof(fa.bases.contents), fa.off[2]) == b"ACGTacgtnTT"
+    assert host.sf_fasta_read(str(tmp_path / "missing.fa").encode(), C.byref(fa), err, 512) != 0
+
+
+def test_model_reader(host, tmp_path):
+    for k in (5, 6):
+        mean, stdv = synth.make_model(k)
+        p = str(tmp_path / f"m{k}.txt")
+        synth.write_model_file(p, k, mean, stdv)
+        lm = C.POINTER(C.c_float)()
+        kk = C.c_uint32()
+        err = C.create_string_buffer(512)
+        assert host.sf_model_read(p.encode(), C.byref(lm), C.byref(kk), err, 512) == 0, err.value
+        assert kk.value == k
+        got = np.ctypeslib.as_array(lm, shape=(4 ** k,))
+        assert np.array_equal(got.view(np.uint32), mean.view(np.uint32))
+    # truncated file
+    bad = str(tmp_path / "bad.txt")
+    open(bad, "w").write("#k\t5\nAAAAA\t1.0\t1.0\n")
+    lm = C.POINTER(C.c_float)()
+    kk = C.c_uint32()
+    err = C.create_string_buffer(512)
+    assert host.sf_model_read(bad.encode(), C.byref(lm), C.byref(kk), err, 512) != 0
+    assert b"prematurely" in err.value
