@@ -191,24 +191,15 @@ def main():
         reference_arm(args)
         return
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-
     import torch
-    import torch.distributed as dist
-    from sigfish_b200 import capi
+    from sigfish_b200 import capi, ranks
 
+    rank, world, local = ranks.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    R = ranks.Ranks(backend="nccl", device=torch.device("cuda", local))
+    barrier = R.barrier
 
     mean, stdv, seq, sigs = make_workload(args.reads, seed=100 + rank, ref_len=args.ref_len)
     from sigfish_b200 import synth
@@ -265,14 +256,10 @@ def main():
     h2d = int(packed[0].nbytes + (2 * len(sigs) + 1) * 8 + 3 * 4 * len(sigs))
     d2h = int(len(sigs) * (40 + 32))
 
-    stats = torch.tensor([ms_step, e2e_ms, dtw / args.steps, evt / args.steps, trc / args.steps, wall_ms / args.steps],
-                         dtype=torch.float64, device="cuda")
-    tot_cells = torch.tensor([cells, float(len(sigs)), float(sum(len(s) for s in sigs))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot_cells, op=dist.ReduceOp.SUM)
-    ms_step, e2e_ms, dtw_ms, evt_ms, trc_ms, wall_step = [float(x) for x in stats.tolist()]
-    job_cells, job_reads, job_samples = [float(x) for x in tot_cells.tolist()]
+    # slowest rank sets the step time; work is summed over ranks
+    ms_step, e2e_ms, dtw_ms, evt_ms, trc_ms, wall_step = R.max(
+        [ms_step, e2e_ms, dtw / args.steps, evt / args.steps, trc / args.steps, wall_ms / args.steps])
+    job_cells, job_reads, job_samples = R.sum([cells, float(len(sigs)), float(sum(len(s) for s in sigs))])
 
     if rank == 0:
         clocks = sampler.result()
@@ -284,7 +271,7 @@ def main():
         peak_naive = sm_count * 4 * clk / SASS_PER_STEP * (32 * ROWS_PER_LANE)
         # padded rows are issued but do no algorithmic work: count only qlen of the 32*R rows
         dtw_cells_per_s = cells / (dtw_ms * 1e-3)
-        value = job_cells / (ms_step * 1e-3) / 1e9
+        value = ranks.job_throughput(job_cells, ms_step)
         line = {
             "metric": "sDTW GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -328,8 +315,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
 
 
 if __name__ == "__main__":

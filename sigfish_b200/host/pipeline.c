@@ -324,6 +324,30 @@ static void parse_db(core_t *core, db_t *db)
     free(tid);
 }
 
+/* Splits n_rec reads into G contiguous ranges [begin[g], begin[g+1]) holding about the same number of
+ * samples each (the per-read device work is dominated by the fixed-size DTW, the copy by the samples; a
+ * contiguous split keeps the output in input order with a plain concatenation). */
+void sf_shard_ranges(int32_t n_rec, const int64_t *n_samples, int32_t G, int32_t *begin)
+{
+    int64_t total = 0;
+    for (int i = 0; i < n_rec; i++)
+        total += n_samples[i];
+    int64_t acc = 0;
+    int g = 0;
+    begin[0] = 0;
+    for (int i = 0; i < n_rec && g + 1 < G; i++) {
+        acc += n_samples[i];
+        while (g + 1 < G && acc * G >= total * (g + 1)) {
+            g++;
+            begin[g] = i + 1;
+        }
+    }
+    while (g < G) {
+        g++;
+        begin[g] = n_rec;
+    }
+}
+
 void submit_db(core_t *core, db_t *db)
 {
     const double t0 = sf_realtime();
@@ -332,23 +356,14 @@ void submit_db(core_t *core, db_t *db)
 
     /* shards: contiguous read ranges with about the same number of samples each */
     const int G = core->num_gpus;
-    int64_t total = 0;
-    for (int i = 0; i < db->n_rec; i++)
-        total += (int64_t)db->rec[i].len_raw_signal;
-    int64_t acc = 0;
-    int g = 0;
-    db->shard_begin[0] = 0;
-    for (int i = 0; i < db->n_rec && g + 1 < G; i++) {
-        acc += (int64_t)db->rec[i].len_raw_signal;
-        if (acc * G >= total * (g + 1)) {
-            g++;
-            db->shard_begin[g] = i + 1;
-        }
+    {
+        int64_t *lens = (int64_t *)malloc(sizeof(int64_t) * (size_t)(db->n_rec > 0 ? db->n_rec : 1));
+        for (int i = 0; i < db->n_rec; i++)
+            lens[i] = (int64_t)db->rec[i].len_raw_signal;
+        sf_shard_ranges(db->n_rec, lens, G, db->shard_begin);
+        free(lens);
     }
-    while (g < G) {
-        g++;
-        db->shard_begin[g] = db->n_rec;
-    }
+    int g;
 
     db->slot = core->next_slot;
     core->next_slot ^= 1;
