@@ -49,10 +49,12 @@ typedef struct {
     int32_t device;       /* CUDA ordinal */
     uint32_t flags;       /* SFGPU_* bits */
     int32_t query_size;   /* -q  (opt.query_size)  */
-    int32_t prefix_size;  /* -p  (opt.prefix_size); <0 is rejected here (auto start is host side) */
+    int32_t prefix_size;  /* -p  (opt.prefix_size); < 0: automatic query start (RNA only: the jnn adaptor /
+                             poly-A finders of src/jnn.c and detect_query_start(), src/sigfish.c:380-422) */
     int32_t kmer_size;    /* core->kmer_size */
     int32_t n_slots;      /* batches in flight (double buffering); 0 -> 2 */
-    int32_t reserved[6];
+    int32_t pore;         /* opt.pore_flag: 0 r9, 1 r10, 2 rna004 (only selects the jnn parameters) */
+    int32_t reserved[5];  /* [0], [1]: test knobs (checkpoint spacing, restart window); keep 0 */
 } sfgpu_opt_t;
 
 /* per-read output of the device stages: what normalise_single() leaves in db->qstart/qend
@@ -62,7 +64,8 @@ typedef struct {
     int64_t n_events;     /* et.n (a lower bound > qend when the block stopped early) */
     int32_t qstart, qend; /* query window in events */
     int32_t qlen;         /* 0: the read prints nothing (empty, ignored or no peak found) */
-    int32_t status;       /* bit0 ignored, bit1 too short, bit2 no peak, bit3 sequential prefix-sum redo */
+    int32_t status;       /* bit0 ignored, bit1 too short, bit2 no peak, bit3 sequential prefix-sum redo,
+                             bit4 automatic query start failed (50-event fall-back, db->prefix_fail) */
     uint64_t start_raw;   /* event[qstart].start */
     uint64_t end_raw;     /* event[qend-1].start + length */
     float score, score2;  /* aln[4].score, aln[3].score */

@@ -30,6 +30,7 @@ extern "C" {
 #define ORC_INV 0x004 /* --invert   */
 #define ORC_REF 0x010 /* --full-ref */
 #define ORC_END 0x020 /* --from-end */
+#define ORC_RNA004 0x400 /* oracle-only bit: pore_flag == OPT_PORE_RNA004 (selects the jnn parameter set) */
 
 /* reference src/sigfish.h:57-63 */
 typedef struct {
@@ -55,6 +56,11 @@ int64_t orc_peaks(const float *t1, const float *t2, int64_t n, int rna, uint64_t
  * or -1 when the reference would hit undefined behaviour (no peak found). */
 int64_t orc_detect_events(const int16_t *raw, int64_t n, float digitisation, float offset,
                           float range, int rna, orc_event_t **out);
+
+/* ---- automatic query start, -p < 0 (reference src/jnn.c, src/sigfish.c:380-422) ---- */
+/* raw-sample index where the poly-A tail ends, or -1 when adaptor / poly-A are not found */
+int64_t orc_polya_end_sample(const int16_t *raw, int64_t n, float digitisation, float offset, float range,
+                             int rna004);
 
 /* ---- reference synthesis (reference src/genref.c:23-241, src/ref.h:13-76) ---- */
 typedef struct {

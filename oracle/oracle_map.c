@@ -212,7 +212,24 @@ void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float dig
     int64_t lo, hi;
     int32_t st;
     int64_t nkeep = nev;
+    int32_t fail = 0;
+    if (p < 0 && !(flags & ORC_END)) { /* sigfish.c:438-447 + detect_query_start 380-422 */
+        const int64_t pe = orc_polya_end_sample(raw, n, digitisation, offset, range, (flags & ORC_RNA004) != 0);
+        int64_t first = -1;
+        if (pe > 0) {
+            int64_t e = 0;
+            while (e < nev && ev[e].start < (uint64_t)pe)
+                e++;
+            first = e < nev ? e : -1;
+        }
+        if (first < 0) {
+            fail = 4; /* prefix_fail: fall back to 50 events */
+            first = 50;
+        }
+        p = (int32_t)first;
+    }
     int go = orc_window_normalise(ev, &nkeep, flags, q, p, &lo, &hi, &st);
+    st |= fail;
     hit->status = st;
     hit->qstart = lo;
     hit->qend = hi;

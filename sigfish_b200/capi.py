@@ -23,7 +23,7 @@ SYMBOLS = ["sfgpu_device_count", "sfgpu_create", "sfgpu_set_ref", "sfgpu_submit"
 class Opt(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("query_size", C.c_int32),
                 ("prefix_size", C.c_int32), ("kmer_size", C.c_int32), ("n_slots", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("pore", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Result(C.Structure):
@@ -94,11 +94,11 @@ class Context:
 
     def __init__(self, level_mean: np.ndarray, kmer_size: int, flags: int = 0, query_size: int = 250,
                  prefix_size: int = 50, device: int = 0, n_slots: int = 2, ck_min_cols: int = 0,
-                 min_window: int = 0):
+                 min_window: int = 0, pore: int = 0):
         L = lib()
         self._h = C.c_void_p()
         self.opt = Opt(device=device, flags=flags, query_size=query_size, prefix_size=prefix_size,
-                       kmer_size=kmer_size, n_slots=n_slots)
+                       kmer_size=kmer_size, n_slots=n_slots, pore=pore)
         self.opt.reserved[0] = ck_min_cols  # test knob: checkpoint segments longer than this
         self.opt.reserved[1] = min_window   # test knob: restart distance of the start-coordinate pass
         lm = np.ascontiguousarray(level_mean, dtype=np.float32)

@@ -49,6 +49,11 @@ struct sf_ev_args {
     int32_t q_cap;
     sf_readinfo *info;          // [n_reads]
     int32_t keep_all;           // 1: never exit early (event-table dumps for tests)
+    // automatic query start (p < 0): raw-sample index where the poly-A tail ends (sf_qstart.cuh), -1 when
+    // the detector found nothing.  Event slots are then split: [0, cap_a) holds events 0..cap_a-1 (the
+    // 50-event fall-back window), [cap_a, ev_cap) the events from the detected start on.
+    const int64_t *polya_end;
+    int32_t cap_a;
 };
 
 struct sf_finder {
@@ -130,7 +135,12 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
     float *ev_mean = a.ev_mean + (size_t)read * cap;
     float *ev_len = a.ev_len + (size_t)read * cap;
     // events needed before the block may stop: boundary index qend-1 must exist
-    const long long need_peaks = (from_end || a.keep_all || a.p < 0) ? (1ll << 62) : (long long)a.p + a.q;
+    const bool autop = a.p < 0 && !a.keep_all;
+    const long long pe = autop ? a.polya_end[read] : -1; // sigfish.c:380-422
+    long long need_peaks = (from_end || a.keep_all) ? (1ll << 62) : (long long)(a.p < 0 ? 50 : a.p) + a.q;
+    if (autop && pe > 0)
+        need_peaks = 1ll << 62; // until the first event at or after the poly-A end is known
+    long long qs = -1;          // index of that event
 
     // sequential state (thread 0 only)
     sf_finder f0, f1;
@@ -284,10 +294,23 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                         const unsigned long long b = (unsigned long long)me.peak_pos;
                         const float len = (float)(b - prev_b);
                         const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(me.peak_sum, prev_s)), len);
-                        const long long slot = npk % cap;
-                        ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                        if (!autop) {
+                            const long long slot = npk % cap;
+                            ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                        } else {
+                            if (npk < a.cap_a) { ev_start[npk] = prev_b; ev_mean[npk] = mean; ev_len[npk] = len; }
+                            if (qs >= 0 && npk - qs < cap - a.cap_a) {
+                                const long long slot = a.cap_a + (npk - qs);
+                                ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                            }
+                        }
                         npk++;
                         prev_b = b; prev_s = me.peak_sum;
+                        // the event that opens here is the first one starting at or after the poly-A end
+                        if (autop && qs < 0 && pe > 0 && b >= (unsigned long long)pe) {
+                            qs = npk;
+                            need_peaks = qs + a.q;
+                        }
                         me.peak_pos = -1;
                         me.peak_val = v;
                         me.valid = 0;
@@ -325,15 +348,31 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
             const long long rel = (n_tiles - 1) * SF_EV_TILE - SF_EV_KEEP;
             const float len = (float)((unsigned long long)n - prev_b);
             const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(S[n - rel], prev_s)), len);
-            const long long slot = npk % cap;
-            ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+            if (!autop) {
+                const long long slot = npk % cap;
+                ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+            } else {
+                if (npk < a.cap_a) { ev_start[npk] = prev_b; ev_mean[npk] = mean; ev_len[npk] = len; }
+                if (qs >= 0 && npk - qs < cap - a.cap_a) {
+                    const long long slot = a.cap_a + (npk - qs);
+                    ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                }
+            }
             nev = npk + 1;
         }
         ri.n_events = nev;
         long long lo = 0, hi = 0, nn = nev;
         if (nn > 0) {
             if (!from_end) { // sigfish.c:435-462
-                lo = a.p < 0 ? 50 : a.p;
+                lo = a.p;
+                if (a.p < 0) {
+                    if (qs >= 0) {
+                        lo = qs;
+                    } else { // detector failed, or no event starts after the poly-A end: 50-event fall-back
+                        lo = 50;
+                        ri.status |= 16;
+                    }
+                }
                 hi = lo + a.q;
                 if (lo + 25 > nn) { lo = hi = 0; nn = 0; ri.status |= 1; }
                 else if (hi > nn) { hi = nn; ri.status |= 2; }
@@ -350,14 +389,18 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         ri.qlen = qlen;
         ri.start_raw = 0; ri.end_raw = 0;
         if (qlen > 0) {
+            // where event j of the window lives: ring slot, or in automatic mode the detected-start area
+            const long long base_q = (autop && qs >= 0) ? (long long)a.cap_a - qs : 0;
+            const bool ring = !autop;
+#define SF_EV_SLOT(j) (ring ? (j) % cap : (j) + base_q)
             // sigfish.c:483-502
             const float cnt = (float)qlen;
             float mean = 0.0f;
-            for (long long j = lo; j < hi; j++) mean = __fadd_rn(mean, ev_mean[j % cap]);
+            for (long long j = lo; j < hi; j++) mean = __fadd_rn(mean, ev_mean[SF_EV_SLOT(j)]);
             mean = __fdiv_rn(mean, cnt);
             float var = 0.0f;
             for (long long j = lo; j < hi; j++) {
-                const float d = __fsub_rn(ev_mean[j % cap], mean);
+                const float d = __fsub_rn(ev_mean[SF_EV_SLOT(j)], mean);
                 var = __fadd_rn(var, __fmul_rn(d, d));
             }
             var = __fdiv_rn(var, cnt);
@@ -365,14 +408,15 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
             float *qv = a.queries + (size_t)read * a.q_cap;
             const bool flip = rna && !(a.flags & SF_INV); // sigfish.c:857-867
             for (long long j = lo; j < hi; j++) {
-                const float z = __fdiv_rn(__fsub_rn(ev_mean[j % cap], mean), sd);
+                const float z = __fdiv_rn(__fsub_rn(ev_mean[SF_EV_SLOT(j)], mean), sd);
                 const int k = (int)(j - lo);
                 qv[flip ? qlen - 1 - k : k] = z;
             }
             // sigfish.c:804-805 (uint64 + float evaluates in fp32)
-            ri.start_raw = ev_start[lo % cap];
+            ri.start_raw = ev_start[SF_EV_SLOT(lo)];
             const long long le = hi - 1;
-            ri.end_raw = (uint64_t)__fadd_rn((float)ev_start[le % cap], ev_len[le % cap]);
+            ri.end_raw = (uint64_t)__fadd_rn((float)ev_start[SF_EV_SLOT(le)], ev_len[SF_EV_SLOT(le)]);
+#undef SF_EV_SLOT
         }
         a.info[read] = ri;
     }

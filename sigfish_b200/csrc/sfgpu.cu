@@ -20,6 +20,7 @@
 #include "../../include/sfgpu.h"
 #include "sf_types.cuh"
 #include "sf_events.cuh"
+#include "sf_qstart.cuh"
 #include "sf_ref.cuh"
 #include "sf_dtw.cuh"
 #include "sf_trace.cuh"
@@ -49,6 +50,7 @@ struct sf_slot {
     uint64_t *d_ev_start = nullptr;
     float *d_ev_mean = nullptr, *d_ev_len = nullptr;
     float *d_queries = nullptr;
+    int64_t *d_polya = nullptr;
     sf_readinfo *d_info = nullptr;
     sf_taskres *d_res = nullptr;
     float *d_ckpt = nullptr;
@@ -66,7 +68,7 @@ struct sf_slot {
 
 struct sfgpu_ctx {
     sfgpu_opt_t opt;
-    int R = 0, q_cap = 0, ev_cap = 0;
+    int R = 0, q_cap = 0, ev_cap = 0, ev_cap_a = 0;
     int sm_count = 0;
     float *d_level_mean = nullptr;
     // reference
@@ -138,7 +140,7 @@ void slot_free_buffers(sf_slot &s)
     hfree(s.h_signal); hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
     dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
-    dfree(s.d_hits);
+    dfree(s.d_hits); dfree(s.d_polya);
     s.cap_reads = 0;
     s.cap_samples = 0;
 }
@@ -158,7 +160,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         const int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
-        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits);
+        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya);
         s.cap_reads = 0;
         const size_t n = (size_t)cap;
         SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
@@ -176,6 +178,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         if (c->ck_per_read > 0)
             SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)((c->R + 1) * 32)));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_polya, sizeof(int64_t) * n));
         s.cap_reads = cap;
     }
     return SFGPU_OK;
@@ -263,6 +266,23 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ea.q_cap = c->q_cap;
         ea.info = s.d_info;
         ea.keep_all = 0;
+        ea.polya_end = s.d_polya;
+        ea.cap_a = c->ev_cap_a;
+        if (c->opt.prefix_size < 0) {
+            sf_qs_args qa;
+            qa.signal = ea.signal;
+            qa.sig_off = ea.sig_off;
+            qa.sig_len = ea.sig_len;
+            qa.digitisation = ea.digitisation;
+            qa.offset = ea.offset;
+            qa.range = ea.range;
+            qa.n_reads = n;
+            qa.rna004 = c->opt.pore == 2;
+            qa.polya_end = s.d_polya;
+            sf_qstart_kernel<<<(n + 31) / 32, 32, 0, st>>>(qa);
+            SF_CUDA(c, cudaGetLastError());
+            s.timing.other_launches++;
+        }
         sf_events_kernel<<<n, SF_EV_THREADS, 0, st>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         s.timing.other_launches++;
@@ -492,8 +512,8 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
     *out = nullptr;
     if (opt->query_size <= 0)
         return fail(nullptr, SFGPU_EARG, "query_size must be positive");
-    if (opt->prefix_size < 0)
-        return fail(nullptr, SFGPU_EARG, "prefix_size < 0 (auto query start) is resolved by the host before the device stages");
+    if (opt->prefix_size < 0 && (!(opt->flags & SFGPU_RNA) || (opt->flags & (SFGPU_INV | SFGPU_END))))
+        return fail(nullptr, SFGPU_EARG, "prefix_size < 0 (automatic query start) needs --rna and excludes --invert / --from-end");
     if (opt->kmer_size < 1 || opt->kmer_size > 12)
         return fail(nullptr, SFGPU_EARG, "kmer_size out of range");
     const int rows = pick_rows(opt->query_size);
@@ -515,7 +535,13 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
     c->opt = *opt;
     c->R = rows;
     c->q_cap = 32 * rows;
-    c->ev_cap = opt->prefix_size + opt->query_size + 4;
+    if (opt->prefix_size >= 0) {
+        c->ev_cap = opt->prefix_size + opt->query_size + 4;
+        c->ev_cap_a = 0;
+    } else { // events 0..50+q for the fall-back window, then q more from the detected start
+        c->ev_cap_a = 50 + opt->query_size + 4;
+        c->ev_cap = c->ev_cap_a + opt->query_size + 4;
+    }
     c->sm_count = prop.multiProcessorCount;
     c->min_window = 2 * opt->query_size;
     if (opt->reserved[0] > 0)
@@ -948,6 +974,8 @@ int64_t sfgpu_event_table(sfgpu_ctx *c, const int16_t *signal, int64_t n_samples
         ea.q_cap = c->q_cap;
         ea.info = d_info;
         ea.keep_all = 1;
+        ea.polya_end = nullptr;
+        ea.cap_a = 0;
         sf_events_kernel<<<1, SF_EV_THREADS>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         SF_CUDA(c, cudaDeviceSynchronize());

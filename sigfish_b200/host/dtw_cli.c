@@ -7,7 +7,7 @@
  *   - --gpus N / --gpu-first I choose the devices (default: all visible B200s); reads are sharded
  *     over them with the reference replicated;
  *   - --pore rna004 is accepted (the reference's validity test rejects it by mistake);
- *   - -p < 0 (auto query start, jnn) and --sam are not implemented yet and are refused with a message;
+ *   - --sam is not implemented yet and is refused with a message;
  *   - --profile-cpu / --accel are accepted and ignored: the stage timers are always printed.
  */
 #include <errno.h>
@@ -207,7 +207,6 @@ int dtw_main(int argc, char *argv[])
             SF_FATAL("%s", "Inversion is not compatible with auto query start detection.");
         if (opt.flag & SIGFISH_END)
             SF_FATAL("%s", "Mapping from query end is not compatible with auto query start detection.");
-        SF_FATAL("%s", "auto query start detection (-p < 0) is not implemented on the B200 path yet");
     }
     if (opt.flag & SIGFISH_SAM)
         SF_FATAL("%s", "--sam is not implemented on the B200 path yet (PAF only)");

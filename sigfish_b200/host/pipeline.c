@@ -181,6 +181,7 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
         go.prefix_size = opt.prefix_size;
         go.kmer_size = (int32_t)core->kmer_size;
         go.n_slots = 2;
+        go.pore = opt.pore_flag;
         if (sfgpu_create(&core->gpu[g], &go, core->level_mean) != SFGPU_OK) {
             SF_FATAL("GPU %d: %s", first + g, sfgpu_strerror(NULL));
         }
@@ -446,6 +447,8 @@ void collect_db(core_t *core, db_t *db)
             db->ignored++;
         if (r->status & 2)
             db->too_short++;
+        if (r->status & 16)
+            db->prefix_fail++;
         if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0)
             continue;
         /* src/sigfish.c:969-985 */

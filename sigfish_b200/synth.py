@@ -205,3 +205,34 @@ def write_blow5(path: str, read_ids, signals, rna: bool = False, kit: str | None
                 rec = zlib.compress(rec)
             f.write(struct.pack("<Q", len(rec)) + rec)
         f.write(b"5WOLB")
+
+
+def simulate_rna_reads_with_tail(seqs, k: int, level_mean: np.ndarray, n_reads: int, seed: int,
+                                 bases_per_read: int = 700, scaling: dict | None = None):
+    """direct-RNA-like reads for the automatic query start (-p -1): a low-current adaptor stretch, a flat
+    poly-A plateau about 30 pA above it, then the transcript body read 3'->5'.  Every fourth read has no
+    tail at all (the detector must fail and fall back to 50 events)."""
+    rng = np.random.default_rng(seed)
+    scaling = scaling or RNA_SCALING
+    ranks_ = [kmer_ranks(s, k) for s in seqs]
+    sigs, truth = [], []
+    for r in range(n_reads):
+        ci = int(rng.integers(0, len(seqs)))
+        n_k = ranks_[ci].shape[0]
+        span = min(bases_per_read, n_k)
+        lv = level_mean[ranks_[ci][n_k - span:]][::-1].astype(np.float64)
+        dwell = 6 + rng.geometric(1.0 / 19.0, size=lv.shape[0]) - 1
+        body = np.repeat(lv, dwell) + rng.normal(0.0, 1.5, size=int(dwell.sum()))
+        if r % 4 != 3:
+            a_len = int(rng.integers(2600, 6000))
+            p_len = int(rng.integers(500, 1800))
+            a_lvl = float(rng.uniform(62.0, 72.0))
+            adaptor = rng.normal(a_lvl, 2.5, size=a_len)
+            polya = rng.normal(a_lvl + 30.0 + rng.uniform(-6, 6), 1.5, size=p_len)
+            pa = np.concatenate([adaptor, polya, body])
+        else:
+            pa = body
+        raw = np.rint(pa * scaling["digitisation"] / scaling["range"] - scaling["offset"])
+        sigs.append(np.clip(raw, -32768, 32767).astype(np.int16))
+        truth.append((ci, "+", n_k - span))
+    return sigs, truth

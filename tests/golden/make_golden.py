@@ -123,6 +123,14 @@ CASES = {
     "rna_sequin_full_ref_from_end": ("sequin_rna", "rnasequin", 5, H.F_RNA | H.F_REF | H.F_END, 250, 50),
     "rna_sequin_q500": ("sequin_rna", "rnasequin", 5, H.F_RNA, 500, 50),
     "rna_synth32": ("synth_rna32", "rnasequin", 5, H.F_RNA, 250, 50),
+    # automatic query start (jnn adaptor / poly-A finders); the first is the reference's own test
+    # configuration (test/test.sh:70)
+    "rna_sequin_q500_auto": ("sequin_rna", "rnasequin", 5, H.F_RNA, 500, -1),
+    "rna_sequin_auto": ("sequin_rna", "rnasequin", 5, H.F_RNA, 250, -1),
+    "rna_sequin_auto_full_ref": ("sequin_rna", "rnasequin", 5, H.F_RNA | H.F_REF, 250, -1),
+    "rna_tail24_auto": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA, 250, -1),
+    "rna_tail24_auto_dtw_std": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA | H.F_DTW, 250, -1),
+    "rna_tail24_p50": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA, 250, 50),
 }
 
 
@@ -176,6 +184,10 @@ def main():
     sigs, _ = synth.simulate_reads(seq_seqs, 5, models[5][0], 32, seed=14, rna=True, bases_per_read=420)
     save_reads(os.path.join(HERE, "synth_rna32.npz"), [f"synth_rna_{i:04d}" for i in range(32)], sigs,
                [synth.RNA_SCALING] * 32)
+
+    sigs, _ = synth.simulate_rna_reads_with_tail(seq_seqs, 5, models[5][0], 24, seed=16)
+    save_reads(os.path.join(HERE, "synth_rna_tail24.npz"), [f"synth_tail_{i:04d}" for i in range(24)], sigs,
+               [synth.RNA_SCALING] * 24)
 
     # 3. golden PAFs from the reference binary
     for k, (mean, stdv) in models.items():

@@ -36,10 +36,13 @@ def assert_hit_equal(g, o, tag, flags, q, p):
         return
     assert g["qlen"] == o.qend - o.qstart, tag
     assert (g["qstart"], g["qend"]) == (o.qstart, o.qend), tag
-    assert (g["status"] & 3) == o.status, tag
+    assert (g["status"] & 3) == (o.status & 3), tag
+    assert bool(g["status"] & 16) == bool(o.status & 4), tag  # automatic query start failed
     assert (int(g["start_raw"]), int(g["end_raw"])) == (o.start_raw, o.end_raw), tag
     if flags & H.F_END:
         assert g["n_events"] == o.n_events, tag
+    elif p < 0:
+        assert g["qend"] < g["n_events"] <= o.n_events or g["n_events"] == o.n_events, tag
     else:
         assert g["n_events"] == min(o.n_events, p + q + 1) or g["n_events"] == o.n_events, tag
     assert g["rid"] == o.rid, tag
@@ -286,4 +289,26 @@ def test_long_reference_round_trip_property():
         g = got[i]
         assert g["score"] == 0.0 and g["strand"] == i // 4
         assert (g["pos_st"], g["pos_end"]) == (s, s + 249)
+    ctx.close()
+
+
+def test_auto_query_start_rna004_parameter_set():
+    """-p -1 with pore_flag == rna004 switches the adaptor finder to jnn.h:91-97 (std_scale 0.7, shortest dip 500)"""
+    c = CASES["rna_tail24_auto"]
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    # shorten some adaptors so that the two parameter sets disagree
+    sigs = [s[1800:] if i % 3 == 0 else s for i, s in enumerate(sigs)]
+    k, q = c["k"], c["q"]
+    ctx = capi.Context(model(k), k, flags=H.F_RNA, query_size=q, prefix_size=-1, pore=2)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    ref = H.OracleRef(seqs, model(k), k, H.F_RNA, q)
+    differs = 0
+    for i, (s, cc) in enumerate(zip(sigs, sc)):
+        o = H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], H.F_RNA | 0x400, q, -1)
+        assert_hit_equal(got[i], o, ("rna004", i), H.F_RNA, q, -1)
+        o9 = H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], H.F_RNA, q, -1)
+        differs += int((o9.qstart, o9.status) != (o.qstart, o.status))
+    ref.close()
     ctx.close()
