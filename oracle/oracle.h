@@ -130,6 +130,14 @@ void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float dig
 int orc_paf_line(char *buf, size_t cap, const orc_hit_t *hit, const char *read_id,
                  const char *rname, int32_t ref_seq_len, int64_t len_raw_signal);
 
+/* sam_str (sigfish.c:770-794) for the hit orc_align() produced from the same normalised events */
+int orc_sam_line(const orc_ref_t *ref, const orc_event_t *ev, uint32_t flags, const orc_hit_t *hit,
+                 const char *read_id, const char *rname, char *buf, size_t cap);
+/* whole read -> SAM line (0 bytes when the read prints nothing) */
+int orc_map_read_sam(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation, float offset,
+                     float range, uint32_t flags, int32_t q, int32_t p, const char *read_id,
+                     const char *const *rnames, char *buf, size_t cap);
+
 void orc_free(void *p);
 
 #ifdef __cplusplus

@@ -195,8 +195,33 @@ void orc_align(const orc_ref_t *ref, const orc_event_t *ev, int64_t qstart, int6
     hit->mapq = (int32_t)(uint8_t)mq; /* aln_t.mapq is uint8_t (sigfish.h:153) */
 }
 
+static void map_read_core(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,
+                          float offset, float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit,
+                          orc_event_t **ev_out);
+
 void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,
                   float offset, float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit)
+{
+    map_read_core(ref, raw, n, digitisation, offset, range, flags, q, p, hit, NULL);
+}
+
+int orc_map_read_sam(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation, float offset,
+                     float range, uint32_t flags, int32_t q, int32_t p, const char *read_id,
+                     const char *const *rnames, char *buf, size_t cap)
+{
+    orc_hit_t hit;
+    orc_event_t *ev = NULL;
+    map_read_core(ref, raw, n, digitisation, offset, range, flags, q, p, &hit, &ev);
+    int len = 0;
+    if (hit.mapped && hit.rid >= 0)
+        len = orc_sam_line(ref, ev, flags, &hit, read_id, rnames[hit.rid], buf, cap);
+    free(ev);
+    return len;
+}
+
+static void map_read_core(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,
+                          float offset, float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit,
+                          orc_event_t **ev_out)
 {
     memset(hit, 0, sizeof(*hit));
     hit->rid = -1;
@@ -241,7 +266,10 @@ void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float dig
         hit->end_raw = (uint64_t)((float)ev[hi - 1].start + ev[hi - 1].length);
         orc_align(ref, ev, lo, hi, flags, hit);
     }
-    free(ev);
+    if (ev_out)
+        *ev_out = ev;
+    else
+        free(ev);
 }
 
 /* sigfish.c:628-660 with the arguments aln_to_str passes (796-826) */
@@ -272,4 +300,143 @@ void orc_align_means(const orc_ref_t *ref, const float *means, int32_t n, uint32
     hit->qend = n;
     orc_align(ref, ev, 0, n, flags, hit);
     free(ev);
+}
+
+/* ---- SAM output (reference src/sigfish.c:530-571 path_to_map, 663-768 r2qevent_map_to_ss, 770-794 sam_str) ---- */
+
+typedef struct {
+    int32_t first, last; /* query events aligned to one reference position, -1/-1: none */
+} span_t;
+
+/* sigfish.c:530-571: walk the warping path in forward order */
+static span_t *spans_from_path(const int32_t *px, const int32_t *py, int32_t k, int32_t len)
+{
+    span_t *sp = (span_t *)malloc(sizeof(span_t) * (size_t)(len > 0 ? len : 1));
+    for (int32_t i = 0; i < len; i++)
+        sp[i].first = sp[i].last = -1;
+    const int32_t origin = py[0];
+    int32_t prev_q = -1;
+    for (int32_t s = 0; s < k; s++) {
+        const int32_t at = py[s] - origin, qi = px[s];
+        if (sp[at].first == -1)
+            sp[at].first = qi;
+        sp[at].last = qi;
+        if (prev_q == qi) /* same query event again (a horizontal step): this position gets nothing */
+            sp[at].first = sp[at].last = -1;
+        prev_q = qi;
+    }
+    return sp;
+}
+
+static int appendf(char *buf, size_t cap, size_t *len, const char *fmt, long v)
+{
+    int w = snprintf(buf + *len, *len < cap ? cap - *len : 0, fmt, v);
+    if (w > 0)
+        *len += (size_t)w;
+    return w;
+}
+
+/* sam_str() for the winning hit of `hit` (as filled by orc_align on the same normalised events).
+ * Returns the number of bytes written. */
+int orc_sam_line(const orc_ref_t *ref, const orc_event_t *ev, uint32_t flags, const orc_hit_t *hit,
+                 const char *read_id, const char *rname, char *buf, size_t cap)
+{
+    const int rna = (flags & ORC_RNA) != 0;
+    const int64_t qstart = hit->qstart, qend = hit->qend;
+    const int qlen = (int)(qend - qstart);
+    const int rlen = ref->ref_lengths[hit->rid];
+    /* rebuild the winner's cost matrix and its path */
+    float *query = (float *)malloc(sizeof(float) * (size_t)qlen);
+    for (int j = 0; j < qlen; j++) {
+        if (rna && !(flags & ORC_INV))
+            query[qlen - 1 - j] = ev[qstart + j].mean;
+        else
+            query[j] = ev[qstart + j].mean;
+    }
+    const float *y = hit->strand == '+' ? ref->forward[hit->rid] : ref->reverse[hit->rid];
+    float *cost = (float *)malloc(sizeof(float) * (size_t)qlen * (size_t)rlen);
+    if (flags & ORC_DTW)
+        orc_std_dtw(query, y, qlen, rlen, cost);
+    else
+        orc_subsequence(query, y, qlen, rlen, cost);
+    int32_t *px = (int32_t *)malloc(sizeof(int32_t) * (size_t)(qlen + rlen));
+    int32_t *py = (int32_t *)malloc(sizeof(int32_t) * (size_t)(qlen + rlen));
+    const int32_t k = orc_path_full(cost, qlen, rlen, hit->raw_pos_end, px, py);
+    const int32_t n_pos = hit->raw_pos_end - hit->raw_pos_st + 1;
+    span_t *sp = spans_from_path(px, py, k, n_pos);
+    free(cost);
+    free(query);
+    free(px);
+    free(py);
+
+    /* sigfish.c:667-695: RNA queries were reversed, map indices back; then make them absolute */
+    if (rna) {
+        const int32_t last = sp[n_pos - 1].last;
+        for (int32_t i = 0; i < n_pos; i++)
+            if (sp[i].first != -1) {
+                sp[i].first = last - sp[i].first;
+                sp[i].last = last - sp[i].last;
+            }
+    }
+    for (int32_t i = 0; i < n_pos; i++)
+        if (sp[i].first != -1) {
+            sp[i].first += (int32_t)qstart;
+            sp[i].last += (int32_t)qstart;
+        }
+    /* sigfish.c:709-721: RNA reports positions back to front, each span swapped */
+    if (rna) {
+        for (int32_t a = 0; a < n_pos / 2; a++) {
+            span_t t = sp[a];
+            sp[a] = sp[n_pos - 1 - a];
+            sp[n_pos - 1 - a] = t;
+        }
+        for (int32_t i = 0; i < n_pos; i++) {
+            int32_t t = sp[i].first;
+            sp[i].first = sp[i].last;
+            sp[i].last = t;
+        }
+    }
+
+    size_t len = 0;
+    /* sigfish.c:770-794 */
+    int w = snprintf(buf, cap, "%s\t%d\t%s\t%ld\t%d\t%ldM\t*\t0\t0\t*\t*\tsi:Z:%ld,%ld,%ld,%ld\tss:Z:", read_id,
+                     hit->strand == '+' ? 0 : 16, rname, (long)hit->pos_st + 1, hit->mapq,
+                     (long)((qend - 1) - qstart), (long)hit->start_raw, (long)hit->end_raw,
+                     (long)(rna ? hit->pos_end : hit->pos_st), (long)(rna ? hit->pos_st : hit->pos_end));
+    if (w > 0)
+        len = (size_t)w;
+    /* sigfish.c:723-762: run-length string over the raw signal: "<n>," match, "<n>D" skipped reference
+     * positions, "<n>I" skipped samples */
+    int64_t cursor = 0, gap = 0;
+    int first_seen = 0;
+    for (int32_t j = 0; j < n_pos; j++) {
+        if (sp[j].first == -1) {
+            if (first_seen)
+                gap++;
+            continue;
+        }
+        const int64_t s0 = (int64_t)ev[sp[j].first].start;
+        const int64_t s1 = (int64_t)ev[sp[j].last].start + (int)ev[sp[j].last].length;
+        first_seen = 1;
+        if (gap > 0) {
+            appendf(buf, cap, &len, "%ldD", (long)gap);
+            gap = 0;
+        }
+        if (j == 0)
+            cursor = s0;
+        int64_t mi = s0 - cursor;
+        cursor += mi;
+        if (mi)
+            appendf(buf, cap, &len, "%ldI", (long)(int)mi);
+        mi = s1 - s0;
+        cursor += mi;
+        if (mi)
+            appendf(buf, cap, &len, "%ld,", (long)(int)mi);
+    }
+    if (len + 1 < cap) {
+        buf[len++] = '\n';
+        buf[len] = 0;
+    }
+    free(sp);
+    return (int)len;
 }

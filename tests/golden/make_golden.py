@@ -134,6 +134,11 @@ CASES = {
 }
 
 
+SAM_CASES = ["dna_sp1_default", "dna_sp1_from_end", "dna_synth48", "dna_multi_contig", "dna_short_reads", "dna_r10_k9",
+             "rna_sequin_default", "rna_sequin_invert", "rna_sequin_full_ref", "rna_sequin_q500_auto",
+             "rna_tail24_auto", "rna_synth32"]
+
+
 def main():
     os.makedirs(os.path.join(HERE, "paf"), exist_ok=True)
     tmp = synth.tmpdir()
@@ -208,6 +213,16 @@ def main():
         print(case, summary[case]["rows"], "rows")
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(summary, f, indent=1, sort_keys=True)
+
+    # 3b. golden SAM (--sam) for a subset
+    os.makedirs(os.path.join(HERE, "sam"), exist_ok=True)
+    for case in SAM_CASES:
+        reads, fasta, k, flags, q, p = CASES[case]
+        sam = H.run_ref(os.path.join(tmp, fasta + ".fa"), os.path.join(tmp, reads + ".slow5"),
+                        os.path.join(tmp, f"model_k{k}.txt"), flags=flags, q=q, p=p, extra=["--sam"])
+        with open(os.path.join(HERE, "sam", case + ".sam"), "w") as f:
+            f.write(sam)
+        print("sam", case, sam.count("\n"), "lines")
 
     # 4. event tables straight from the reference's getevents()
     for name, rna in (("sp1_dna", False), ("sequin_rna", True), ("synth_dna_short", False)):

@@ -97,6 +97,10 @@ def oracle():
                                C.c_int32, C.c_int64]
     L.orc_paf_line.restype = C.c_int
     L.orc_free.argtypes = [C.c_void_p]
+    L.orc_map_read_sam.argtypes = [C.c_void_p, _i16p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_int32,
+                                   C.c_int32, C.c_char_p, C.POINTER(C.c_char_p), C.c_char_p, C.c_size_t]
+    L.orc_polya_end_sample.argtypes = [_i16p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int]
+    L.orc_polya_end_sample.restype = C.c_int64
     _oracle = L
     return L
 
@@ -204,6 +208,21 @@ def oracle_paf(names, seqs, level_mean, k, read_ids, signals, scalings, flags, q
         hit = orc_map(ref, sig, sc["digitisation"], sc["offset"], sc["range"], flags, q, p)
         if hit.mapped:
             out.append(orc_paf(hit, rid, names[hit.rid], int(ref.seq_lens[hit.rid]), len(sig)))
+    ref.close()
+    return "".join(out)
+
+
+def oracle_sam(names, seqs, level_mean, k, read_ids, signals, scalings, flags, q=250, p=50) -> str:
+    """Whole `sigfish dtw --sam` run through the oracle -> SAM text (header + records)."""
+    ref = OracleRef(seqs, level_mean, k, flags, q)
+    out = [f"@SQ\tSN:{names[i]}\tLN:{ref.length(i)}\n" for i in range(ref.n)]
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    buf = C.create_string_buffer(1 << 20)
+    for rid, sig, sc in zip(read_ids, signals, scalings):
+        raw = np.ascontiguousarray(sig, dtype=np.int16)
+        n = oracle().orc_map_read_sam(ref.h, raw, raw.shape[0], np.float32(sc["digitisation"]), np.float32(sc["offset"]),
+                                      np.float32(sc["range"]), flags, q, p, rid.encode(), arr, buf, 1 << 20)
+        out.append(buf.raw[:n].decode())
     ref.close()
     return "".join(out)
 

@@ -146,3 +146,18 @@ def test_top_list_later_equal_score_wins():
     for sig in sigs:
         hit = H.orc_map(ref, sig, 8192.0, 10.0, 1402.882, 0, 250, 50)
         assert hit.mapped and hit.rid == 1 and hit.score == hit.score2 and hit.mapq == 0
+
+
+SAM_CASES = sorted(f[:-4] for f in os.listdir(os.path.join(H.GOLDEN, "sam")))
+
+
+@pytest.mark.parametrize("case", SAM_CASES)
+def test_oracle_sam_matches_reference_golden(case):
+    """--sam: the winner's full warping path turned into the ss:Z string (sigfish.c:530-571, 663-794)"""
+    c = CASES[case]
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    got = H.oracle_sam(names, seqs, model(c["k"]), c["k"], ids, sigs, sc, c["flags"], c["q"], c["p"])
+    want = open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()
+    want = "".join(l for l in want.splitlines(keepends=True) if not l.startswith("@PG"))
+    assert got == want
