@@ -113,6 +113,18 @@ int sfgpu_resubmit(sfgpu_ctx *ctx, int32_t slot);
  * input order).  out has room for the n_reads given to sfgpu_submit. */
 int sfgpu_collect(sfgpu_ctx *ctx, int32_t slot, sfgpu_result_t *out);
 
+/* --sam (contexts created with SFGPU_SAM), after sfgpu_collect(): the full warping path of every read's
+ * winning hit -- what update_aln() keeps as r2qevent_map via subsequence_path() + path_to_map()
+ * (src/sigfish.c:530-571, 599-618; src/cdtw.c:98-167, 192-227) -- and the window's event boundaries
+ * that r2qevent_map_to_ss() reads (src/sigfish.c:737-742).
+ *   moves[move_off[i] .. move_off[i] + n_moves[i])  the path of read i BACKWARDS from the cell
+ *       (qlen-1, pos_end): 0 = diagonal (i-1, j-1), 1 = left (i, j-1), 2 = up (i-1, j); it ends on row 0 at
+ *       column pos_st.  The caller sizes move_off so that read i has room for qlen + pos_end - pos_st
+ *       moves; n_moves[i] = -1 for reads without a hit.
+ *   ev_start / ev_len [i * query_size + k]  event qstart + k of read i (start sample, length). */
+int sfgpu_collect_paths(sfgpu_ctx *ctx, int32_t slot, const int64_t *move_off, uint8_t *moves,
+                        int32_t *n_moves, uint64_t *ev_start, float *ev_len);
+
 /* CUDA-event timings of the slot's last completed batch */
 int sfgpu_timing(sfgpu_ctx *ctx, int32_t slot, sfgpu_timing_t *t);
 

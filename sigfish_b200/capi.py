@@ -17,7 +17,7 @@ SFGPU_RNA, SFGPU_DTW, SFGPU_INV, SFGPU_REF, SFGPU_END, SFGPU_SAM = 0x001, 0x002,
 SYMBOLS = ["sfgpu_device_count", "sfgpu_create", "sfgpu_set_ref", "sfgpu_submit", "sfgpu_resubmit",
            "sfgpu_collect", "sfgpu_timing", "sfgpu_destroy", "sfgpu_strerror", "sfgpu_ref_events",
            "sfgpu_event_table", "sfgpu_query", "sfgpu_ref_columns", "sfgpu_set_ref_events",
-           "sfgpu_submit_queries"]
+           "sfgpu_submit_queries", "sfgpu_collect_paths"]
 
 
 class Opt(C.Structure):
@@ -75,6 +75,7 @@ def lib():
     L.sfgpu_query.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32]
     L.sfgpu_set_ref_events.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
     L.sfgpu_submit_queries.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    L.sfgpu_collect_paths.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_ref_columns.argtypes = [vp]
     L.sfgpu_ref_columns.restype = C.c_int64
     _lib = L
@@ -186,6 +187,34 @@ class Context:
         out = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
         self._check(lib().sfgpu_collect(self._h, slot, _ptr(out)), "sfgpu_collect")
         return out[:n]
+
+    def collect_paths(self, slot, results: np.ndarray):
+        """--sam: per read (px, py) of the winner's warping path in forward order plus the window's event
+        starts / lengths; `results` is what collect(slot) returned"""
+        n = len(results)
+        q = self.opt.query_size
+        need = np.where(results["qlen"] > 0, results["qlen"] + results["pos_end"] - results["pos_st"], 0).astype(np.int64)
+        need = np.maximum(need, 0)
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(need)
+        moves = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        n_moves = np.zeros(max(n, 1), dtype=np.int32)
+        ev_start = np.zeros(max(n, 1) * q, dtype=np.uint64)
+        ev_len = np.zeros(max(n, 1) * q, dtype=np.float32)
+        self._check(lib().sfgpu_collect_paths(self._h, slot, _ptr(off), _ptr(moves), _ptr(n_moves), _ptr(ev_start),
+                                              _ptr(ev_len)), "sfgpu_collect_paths")
+        paths = []
+        for i in range(n):
+            if n_moves[i] < 0:
+                paths.append(None)
+                continue
+            mv = moves[off[i]:off[i] + n_moves[i]]
+            di = np.where(mv == 1, 0, 1)
+            dj = np.where(mv == 2, 0, 1)
+            px = int(results["qlen"][i]) - 1 - np.concatenate([[0], np.cumsum(di)])
+            py = int(results["pos_end"][i]) - np.concatenate([[0], np.cumsum(dj)])
+            paths.append((px[::-1].astype(np.int32), py[::-1].astype(np.int32)))
+        return paths, ev_start.reshape(-1, q)[:n], ev_len.reshape(-1, q)[:n]
 
     def timing(self, slot) -> Timing:
         t = Timing()

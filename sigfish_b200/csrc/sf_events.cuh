@@ -54,6 +54,10 @@ struct sf_ev_args {
     // 50-event fall-back window), [cap_a, ev_cap) the events from the detected start on.
     const int64_t *polya_end;
     int32_t cap_a;
+    // --sam: start sample and length of every event of the query window, in event order (what
+    // r2qevent_map_to_ss() reads from the event table, sigfish.c:737-742); null otherwise
+    uint64_t *win_start;        // [n_reads][q_cap]
+    float *win_len;             // [n_reads][q_cap]
 };
 
 struct sf_finder {
@@ -411,6 +415,10 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                 const float z = __fdiv_rn(__fsub_rn(ev_mean[SF_EV_SLOT(j)], mean), sd);
                 const int k = (int)(j - lo);
                 qv[flip ? qlen - 1 - k : k] = z;
+                if (a.win_start) {
+                    a.win_start[(size_t)read * a.q_cap + k] = ev_start[SF_EV_SLOT(j)];
+                    a.win_len[(size_t)read * a.q_cap + k] = ev_len[SF_EV_SLOT(j)];
+                }
             }
             // sigfish.c:804-805 (uint64 + float evaluates in fp32)
             ri.start_raw = ev_start[SF_EV_SLOT(lo)];

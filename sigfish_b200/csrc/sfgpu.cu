@@ -24,6 +24,7 @@
 #include "sf_ref.cuh"
 #include "sf_dtw.cuh"
 #include "sf_trace.cuh"
+#include "sf_path.cuh"
 
 namespace {
 
@@ -51,6 +52,8 @@ struct sf_slot {
     float *d_ev_mean = nullptr, *d_ev_len = nullptr;
     float *d_queries = nullptr;
     int64_t *d_polya = nullptr;
+    uint64_t *d_win_start = nullptr; // --sam only
+    float *d_win_len = nullptr;
     sf_readinfo *d_info = nullptr;
     sf_taskres *d_res = nullptr;
     float *d_ckpt = nullptr;
@@ -140,7 +143,7 @@ void slot_free_buffers(sf_slot &s)
     hfree(s.h_signal); hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
     dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
-    dfree(s.d_hits); dfree(s.d_polya);
+    dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
     s.cap_reads = 0;
     s.cap_samples = 0;
 }
@@ -160,7 +163,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         const int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
-        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya);
+        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
         s.cap_reads = 0;
         const size_t n = (size_t)cap;
         SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
@@ -179,6 +182,10 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
             SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)((c->R + 1) * 32)));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
         SF_CUDA(c, cudaMalloc(&s.d_polya, sizeof(int64_t) * n));
+        if (c->opt.flags & SFGPU_SAM) {
+            SF_CUDA(c, cudaMalloc(&s.d_win_start, sizeof(uint64_t) * n * c->q_cap));
+            SF_CUDA(c, cudaMalloc(&s.d_win_len, sizeof(float) * n * c->q_cap));
+        }
         s.cap_reads = cap;
     }
     return SFGPU_OK;
@@ -197,6 +204,14 @@ template <int R, bool STD>
 cudaError_t launch_dtw(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
 {
     sf_dtw_score_kernel<R, STD><<<grid, SF_DTW_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaStream_t st)
+{
+    const int warps = 4;
+    const int grid = (a.n_reads + warps - 1) / warps;
+    sf_path_kernel<R, STD><<<grid, warps * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -268,6 +283,8 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ea.keep_all = 0;
         ea.polya_end = s.d_polya;
         ea.cap_a = c->ev_cap_a;
+        ea.win_start = s.d_win_start;
+        ea.win_len = s.d_win_len;
         if (c->opt.prefix_size < 0) {
             sf_qs_args qa;
             qa.signal = ea.signal;
@@ -890,6 +907,106 @@ int sfgpu_collect(sfgpu_ctx *c, int32_t slot, sfgpu_result_t *out)
     return SFGPU_OK;
 }
 
+int sfgpu_collect_paths(sfgpu_ctx *c, int32_t slot, const int64_t *move_off, uint8_t *moves,
+                        int32_t *n_moves, uint64_t *ev_start, float *ev_len)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (!(c->opt.flags & SFGPU_SAM))
+        return fail(c, SFGPU_ESTATE, "sfgpu_collect_paths needs a context created with SFGPU_SAM");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!s.done || s.queries_only)
+        return fail(c, SFGPU_ESTATE, "sfgpu_collect_paths: slot holds no finished read batch");
+    const int n = s.n_reads;
+    if (n == 0)
+        return SFGPU_OK;
+    if (!move_off || !moves || !n_moves || !ev_start || !ev_len)
+        return fail(c, SFGPU_EARG, "null output array");
+    const bool std_dtw = (c->opt.flags & SFGPU_DTW) != 0;
+    const int q = c->opt.query_size;
+    // columns each read's direction window needs, and the caller's move capacity
+    std::vector<int64_t> dir_off(n);
+    int64_t cols = 0;
+    for (int i = 0; i < n; i++) {
+        const sf_hit &h = s.h_hits[i];
+        const int qlen = s.h_info[i].qlen;
+        dir_off[i] = -1;
+        if (qlen <= 0 || h.seg < 0 || h.pos_st < 0 || h.pos_end < h.pos_st)
+            continue;
+        const int64_t width = (int64_t)h.pos_end - (std_dtw ? 0 : h.pos_st) + 1;
+        const int64_t need = (int64_t)qlen + h.pos_end - h.pos_st;
+        if (move_off[i + 1] - move_off[i] < need)
+            return fail(c, SFGPU_EARG, "move buffer of read %d holds %lld entries, %lld needed", i,
+                        (long long)(move_off[i + 1] - move_off[i]), (long long)need);
+        dir_off[i] = cols;
+        cols += width;
+    }
+    const int64_t total_moves = move_off[n];
+    unsigned long long *d_dirs = nullptr;
+    int64_t *d_dir_off = nullptr, *d_move_off = nullptr;
+    uint8_t *d_moves = nullptr;
+    int32_t *d_n = nullptr, *d_sc = nullptr;
+    std::vector<int32_t> start_col(n);
+    std::vector<uint64_t> ws((size_t)n * c->q_cap);
+    std::vector<float> wl((size_t)n * c->q_cap);
+    rc = [&]() -> int {
+        SF_CUDA(c, cudaMalloc(&d_dirs, sizeof(unsigned long long) * 32 * (size_t)std::max<int64_t>(cols, 1)));
+        SF_CUDA(c, cudaMalloc(&d_dir_off, sizeof(int64_t) * n));
+        SF_CUDA(c, cudaMalloc(&d_move_off, sizeof(int64_t) * (n + 1)));
+        SF_CUDA(c, cudaMalloc(&d_moves, (size_t)std::max<int64_t>(total_moves, 1)));
+        SF_CUDA(c, cudaMalloc(&d_n, sizeof(int32_t) * n));
+        SF_CUDA(c, cudaMalloc(&d_sc, sizeof(int32_t) * n));
+        SF_CUDA(c, cudaMemcpyAsync(d_dir_off, dir_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, s.stream));
+        SF_CUDA(c, cudaMemcpyAsync(d_move_off, move_off, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, s.stream));
+        sf_path_args pa;
+        pa.stream = c->d_stream;
+        pa.segs = c->d_segs;
+        pa.queries = s.d_queries;
+        pa.info = s.d_info;
+        pa.q_cap = c->q_cap;
+        pa.hits = s.d_hits;
+        pa.n_reads = n;
+        pa.dir_off = d_dir_off;
+        pa.dirs = d_dirs;
+        pa.move_off = d_move_off;
+        pa.moves = d_moves;
+        pa.n_moves = d_n;
+        pa.start_col = d_sc;
+        cudaError_t e = cudaErrorInvalidValue;
+        SF_DISPATCH_R(c->R, std_dtw, (e = launch_path<R, STD>(pa, s.stream)));
+        SF_CUDA(c, e);
+        if (total_moves > 0)
+            SF_CUDA(c, cudaMemcpyAsync(moves, d_moves, (size_t)total_moves, cudaMemcpyDeviceToHost, s.stream));
+        SF_CUDA(c, cudaMemcpyAsync(n_moves, d_n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
+        SF_CUDA(c, cudaMemcpyAsync(start_col.data(), d_sc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
+        SF_CUDA(c, cudaMemcpyAsync(ws.data(), s.d_win_start, sizeof(uint64_t) * ws.size(), cudaMemcpyDeviceToHost, s.stream));
+        SF_CUDA(c, cudaMemcpyAsync(wl.data(), s.d_win_len, sizeof(float) * wl.size(), cudaMemcpyDeviceToHost, s.stream));
+        SF_CUDA(c, cudaStreamSynchronize(s.stream));
+        return SFGPU_OK;
+    }();
+    dfree(d_dirs); dfree(d_dir_off); dfree(d_move_off); dfree(d_moves); dfree(d_n); dfree(d_sc);
+    if (rc != SFGPU_OK)
+        return rc;
+    for (int i = 0; i < n; i++) {
+        const int qlen = s.h_info[i].qlen;
+        for (int k = 0; k < q; k++) {
+            ev_start[(size_t)i * q + k] = k < qlen ? ws[(size_t)i * c->q_cap + k] : 0;
+            ev_len[(size_t)i * q + k] = k < qlen ? wl[(size_t)i * c->q_cap + k] : 0.0f;
+        }
+        // the backtrack must end where the start-pointer pass said it would
+        if (n_moves[i] >= 0 && start_col[i] != s.h_hits[i].pos_st)
+            return fail(c, SFGPU_ECUDA, "internal: path of read %d starts at column %d, start-coordinate pass gave %d", i,
+                        start_col[i], s.h_hits[i].pos_st);
+    }
+    return SFGPU_OK;
+}
+
 int sfgpu_timing(sfgpu_ctx *c, int32_t slot, sfgpu_timing_t *t)
 {
     if (!c || !t)
@@ -976,6 +1093,8 @@ int64_t sfgpu_event_table(sfgpu_ctx *c, const int16_t *signal, int64_t n_samples
         ea.keep_all = 1;
         ea.polya_end = nullptr;
         ea.cap_a = 0;
+        ea.win_start = nullptr;
+        ea.win_len = nullptr;
         sf_events_kernel<<<1, SF_EV_THREADS>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         SF_CUDA(c, cudaDeviceSynchronize());

@@ -7,7 +7,6 @@
  *   - --gpus N / --gpu-first I choose the devices (default: all visible B200s); reads are sharded
  *     over them with the reference replicated;
  *   - --pore rna004 is accepted (the reference's validity test rejects it by mistake);
- *   - --sam is not implemented yet and is refused with a message;
  *   - --profile-cpu / --accel are accepted and ignored: the stage timers are always printed.
  */
 #include <errno.h>
@@ -95,7 +94,7 @@ static void print_help_msg(FILE *fp, const opt_t *opt)
     fprintf(fp, "   --invert                   reverse the reference events instead of query\n");
     fprintf(fp, "   --full-ref                 map to the full reference\n");
     fprintf(fp, "   --from-end                 Map the end portion of the query instead of the beginning\n");
-    fprintf(fp, "   --sam                      Output in SAM format (not available yet on the B200 path)\n");
+    fprintf(fp, "   --sam                      Output in SAM format\n");
 }
 
 int dtw_main(int argc, char *argv[])
@@ -208,12 +207,12 @@ int dtw_main(int argc, char *argv[])
         if (opt.flag & SIGFISH_END)
             SF_FATAL("%s", "Mapping from query end is not compatible with auto query start detection.");
     }
-    if (opt.flag & SIGFISH_SAM)
-        SF_FATAL("%s", "--sam is not implemented on the B200 path yet (PAF only)");
 
     core_t *core = init_core(fastafile, slow5file, opt, realtime0);
     /* two batches: one on the GPUs, one being loaded */
     db_t *db[2] = {init_db(core), init_db(core)};
+    if (core->opt.flag & SIGFISH_SAM)
+        sam_hdr_wr(core->ref);
     int32_t counter = 0;
     int cur = 0;
     ret_status_t status = load_db(core, db[cur]);

@@ -13,6 +13,7 @@
  */
 #include <math.h>
 #include <pthread.h>
+#include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/resource.h>
@@ -233,6 +234,12 @@ db_t *init_db(core_t *core)
     db->dig = (float *)calloc(n, sizeof(float));
     db->off = (float *)calloc(n, sizeof(float));
     db->rng = (float *)calloc(n, sizeof(float));
+    if (core->opt.flag & SIGFISH_SAM) {
+        db->move_off = (int64_t *)calloc(n + 1, sizeof(int64_t));
+        db->n_moves = (int32_t *)calloc(n, sizeof(int32_t));
+        db->win_start = (uint64_t *)calloc(n * (size_t)core->opt.query_size, sizeof(uint64_t));
+        db->win_len = (float *)calloc(n * (size_t)core->opt.query_size, sizeof(float));
+    }
     return db;
 }
 
@@ -418,6 +425,128 @@ static char *paf_str(const aln_t *aln, const char *read_id, const char *rname, u
     return s;
 }
 
+/* ---- SAM (src/sigfish.c:530-571 path_to_map, 663-768 r2qevent_map_to_ss, 770-794 sam_str) ---- */
+
+typedef struct {
+    int32_t start, stop; /* index_pair_t, src/sigfish.h:141-144 */
+} index_pair_t;
+
+typedef struct {
+    char *s;
+    size_t l, m;
+} sbuf_t;
+
+static void sbuf_printf(sbuf_t *b, const char *fmt, ...)
+{
+    for (;;) {
+        va_list ap;
+        va_start(ap, fmt);
+        const int w = vsnprintf(b->s + b->l, b->m - b->l, fmt, ap);
+        va_end(ap);
+        if (w >= 0 && (size_t)w < b->m - b->l) {
+            b->l += (size_t)w;
+            return;
+        }
+        b->m = b->m * 2 + (size_t)(w > 0 ? w : 64);
+        b->s = (char *)realloc(b->s, b->m);
+    }
+}
+
+/* moves: the winner's path backwards from (qlen-1, pos_end), as sfgpu_collect_paths() returns it */
+static char *sam_str(const aln_t *aln, const sfgpu_result_t *r, const uint8_t *moves, int32_t n_moves,
+                     const uint64_t *ev_start, const float *ev_len, const char *read_id, const char *rname, int rna)
+{
+    const int32_t n_kmers = r->pos_end - r->pos_st + 1;
+    index_pair_t *map = (index_pair_t *)malloc(sizeof(index_pair_t) * (size_t)n_kmers);
+    for (int32_t i = 0; i < n_kmers; i++)
+        map[i].start = map[i].stop = -1;
+    /* forward order: undo the moves from the far end */
+    const int32_t k = n_moves + 1;
+    int32_t *px = (int32_t *)malloc(sizeof(int32_t) * (size_t)k), *py = (int32_t *)malloc(sizeof(int32_t) * (size_t)k);
+    {
+        int32_t i = r->qlen - 1, j = r->pos_end;
+        px[k - 1] = i;
+        py[k - 1] = j;
+        for (int32_t s = 0; s < n_moves; s++) {
+            if (moves[s] == 0) { i--; j--; }
+            else if (moves[s] == 1) { j--; }
+            else { i--; }
+            px[k - 2 - s] = i;
+            py[k - 2 - s] = j;
+        }
+    }
+    int32_t prev_q = -1;
+    for (int32_t s = 0; s < k; s++) { /* path_to_map */
+        const int32_t at = py[s] - py[0], qi = px[s];
+        if (map[at].start == -1)
+            map[at].start = qi;
+        map[at].stop = qi;
+        if (prev_q == qi)
+            map[at].start = map[at].stop = -1;
+        prev_q = qi;
+    }
+    free(px);
+    free(py);
+
+    /* r2qevent_map_to_ss: event indices relative to the window here (the reference adds qstart and indexes
+     * the full event table; ev_start/ev_len hold the window only) */
+    if (rna) {
+        const int32_t end = map[n_kmers - 1].stop;
+        for (int32_t i = 0; i < n_kmers; i++)
+            if (map[i].start != -1) {
+                map[i].start = end - map[i].start;
+                map[i].stop = end - map[i].stop;
+            }
+        for (int32_t a = 0; a < n_kmers / 2; a++) {
+            index_pair_t t = map[a];
+            map[a] = map[n_kmers - 1 - a];
+            map[n_kmers - 1 - a] = t;
+        }
+        for (int32_t i = 0; i < n_kmers; i++) {
+            int32_t t = map[i].start;
+            map[i].start = map[i].stop;
+            map[i].stop = t;
+        }
+    }
+
+    sbuf_t b;
+    b.m = 4000;
+    b.l = 0;
+    b.s = (char *)malloc(b.m);
+    const uint64_t qsize = (uint64_t)(r->qend - 1) - (uint64_t)r->qstart;
+    sbuf_printf(&b, "%s\t%d\t%s\t%ld\t%d\t%ldM\t*\t0\t0\t*\t*\t", read_id, aln->d == '+' ? 0 : 16, rname,
+                (long)aln->pos_st + 1, aln->mapq, (long)qsize);
+    sbuf_printf(&b, "si:Z:%ld,%ld,%ld,%ld\tss:Z:", (long)r->start_raw, (long)r->end_raw,
+                (long)(rna ? aln->pos_end : aln->pos_st), (long)(rna ? aln->pos_st : aln->pos_end));
+    int64_t ci = 0, mi = 0, d = 0;
+    int ff = 1;
+    for (int32_t j = 0; j < n_kmers; j++) {
+        if (map[j].start == -1) {
+            if (!ff)
+                d++;
+            continue;
+        }
+        const int64_t s0 = (int64_t)ev_start[map[j].start];
+        const int64_t s1 = (int64_t)ev_start[map[j].stop] + (int)ev_len[map[j].stop];
+        ff = 0;
+        if (d > 0) {
+            sbuf_printf(&b, "%dD", (int)d);
+            d = 0;
+        }
+        if (j == 0)
+            ci = s0;
+        ci += (mi = s0 - ci);
+        if (mi)
+            sbuf_printf(&b, "%dI", (int)mi);
+        ci += (mi = s1 - s0);
+        if (mi)
+            sbuf_printf(&b, "%d,", (int)mi);
+    }
+    sbuf_printf(&b, "\n");
+    free(map);
+    return b.s;
+}
+
 void collect_db(core_t *core, db_t *db)
 {
     if (!db->submitted)
@@ -426,6 +555,30 @@ void collect_db(core_t *core, db_t *db)
         const int b = db->shard_begin[g];
         if (sfgpu_collect(core->gpu[g], db->slot, db->res + b) != SFGPU_OK) {
             SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
+        }
+        if (core->opt.flag & SIGFISH_SAM) { /* the winners' warping paths + window event boundaries */
+            const int e = db->shard_begin[g + 1];
+            const int q = core->opt.query_size;
+            db->move_off[b] = b == 0 ? 0 : db->move_off[b];
+            for (int i = b; i < e; i++) {
+                const sfgpu_result_t *r = &db->res[i];
+                const int64_t need = r->qlen > 0 && r->rid >= 0 && r->pos_st >= 0 ? (int64_t)r->qlen + r->pos_end - r->pos_st : 0;
+                db->move_off[i + 1] = db->move_off[i] + need;
+            }
+            const int64_t base = db->move_off[b];
+            if ((size_t)db->move_off[e] > db->moves_cap) {
+                db->moves_cap = (size_t)db->move_off[e] * 2 + 4096;
+                db->moves = (uint8_t *)realloc(db->moves, db->moves_cap);
+            }
+            /* offsets relative to the shard */
+            int64_t *rel = (int64_t *)malloc(sizeof(int64_t) * (size_t)(e - b + 1));
+            for (int i = b; i <= e; i++)
+                rel[i - b] = db->move_off[i] - base;
+            if (sfgpu_collect_paths(core->gpu[g], db->slot, rel, db->moves + base, db->n_moves + b,
+                                    db->win_start + (size_t)b * q, db->win_len + (size_t)b * q) != SFGPU_OK) {
+                SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
+            }
+            free(rel);
         }
         sfgpu_timing_t t;
         if (sfgpu_timing(core->gpu[g], db->slot, &t) == SFGPU_OK) {
@@ -469,8 +622,17 @@ void collect_db(core_t *core, db_t *db)
         a->mapq = (uint8_t)mq;
         /* src/sigfish.c:800-807: query_size = (qend-1) - qstart */
         const uint64_t query_size = (uint64_t)(r->qend - 1) - (uint64_t)r->qstart;
-        db->out[i] = paf_str(a, db->rec[i].read_id, ref->ref_names[r->rid], r->start_raw, r->end_raw, query_size,
-                             db->rec[i].len_raw_signal, (uint64_t)ref->ref_seq_lengths[r->rid]);
+        if (core->opt.flag & SIGFISH_SAM) {
+            if (db->n_moves[i] < 0)
+                continue;
+            const int q = core->opt.query_size;
+            db->out[i] = sam_str(a, r, db->moves + db->move_off[i], db->n_moves[i], db->win_start + (size_t)i * q,
+                                 db->win_len + (size_t)i * q, db->rec[i].read_id, ref->ref_names[r->rid],
+                                 (core->opt.flag & SIGFISH_RNA) != 0);
+        } else {
+            db->out[i] = paf_str(a, db->rec[i].read_id, ref->ref_names[r->rid], r->start_raw, r->end_raw, query_size,
+                                 db->rec[i].len_raw_signal, (uint64_t)ref->ref_seq_lengths[r->rid]);
+        }
     }
 }
 
@@ -514,6 +676,7 @@ void free_db(db_t *db)
     }
     free(db->mem_records); free(db->mem_bytes); free(db->mem_cap); free(db->rec); free(db->res); free(db->aln);
     free(db->out); free(db->sig_off); free(db->dig); free(db->off); free(db->rng);
+    free(db->move_off); free(db->n_moves); free(db->win_start); free(db->win_len); free(db->moves);
     free(db);
 }
 
@@ -521,5 +684,6 @@ void sam_hdr_wr(const refsynth_t *ref)
 {
     /* src/dtw_main.c:118-123: LN is the k-mer count, as in the reference */
     for (int i = 0; i < ref->num_ref; i++)
-        printf("@SQ\tSN:%s\tLN:%d\n", ref->ref_names[i], ref->ref_lengths[i]);
+        printf("@SQ\tSN:%s\tLN:%ld\n", ref->ref_names[i], (long)ref->ref_lengths[i]);
+    printf("@PG\tID:sigfish\tPN:sigfish\tVN:%s\n", SFHOST_VERSION_SHORT);
 }

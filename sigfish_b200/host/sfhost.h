@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 #define SFHOST_VERSION "0.1.0-b200 (sigfish 0.2.0 dtw path)"
+#define SFHOST_VERSION_SHORT "0.2.0-b200"
 
 /* option flags: same bits as the reference (src/sigfish.h:30-39) */
 #define SIGFISH_RNA 0x001
@@ -113,6 +114,13 @@ typedef struct {
     int64_t *sig_off;
     float *dig, *off, *rng;
     int32_t shard_begin[SFHOST_MAX_GPUS + 1];
+    /* --sam: winners' paths and window event boundaries */
+    int64_t *move_off;
+    uint8_t *moves;
+    size_t moves_cap;
+    int32_t *n_moves;
+    uint64_t *win_start;
+    float *win_len;
     int32_t slot;        /* device slot this batch was submitted to */
     int submitted;
     /* stats */

@@ -98,3 +98,17 @@ def test_cli_errors_like_the_reference(cli, tmp_path):
     assert r.returncode != 0 and "Usage: sigfish dtw" in r.stderr
     r = subprocess.run([cli, "dtw", fa, str(tmp_path / "missing.blow5"), "--kmer-model", mf], capture_output=True, text=True)
     assert r.returncode != 0 and "Error opening SLOW5 file" in r.stderr
+
+
+SAM_CASES = sorted(f[:-4] for f in os.listdir(os.path.join(H.GOLDEN, "sam")))
+
+
+@pytest.mark.parametrize("case", SAM_CASES)
+def test_cli_sam_is_byte_identical_to_reference(cli, tmp_path, case):
+    """--sam: @SQ header + one record per read with the si:Z / ss:Z tags (needs the winner's full warping path)"""
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, _ = _run(cli, c, fa, reads, mf, ["--sam", "-K", "5"])
+    want = open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()
+    strip = lambda t: "".join(l for l in t.splitlines(keepends=True) if not l.startswith("@PG"))
+    assert strip(out) == strip(want)
+    assert out.count("@PG\tID:sigfish") == 1

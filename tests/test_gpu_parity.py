@@ -312,3 +312,43 @@ def test_auto_query_start_rna004_parameter_set():
         differs += int((o9.qstart, o9.status) != (o.qstart, o.status))
     ref.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("q", [33, 250, 300])
+@pytest.mark.parametrize("quant", [0, 2])
+def test_warping_paths_match_oracle_backtrack(q, quant):
+    """--sam support: sfgpu_collect_paths() must return exactly the path subsequence_path() finds in the full
+    cost matrix (cdtw.c:98-167, 192-227), ties included; checked through real reads so that the event kernel
+    also fills the window boundaries"""
+    c = CASES["dna_multi_contig"]
+    names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    k = c["k"]
+    lm = model(k)
+    if quant:  # a coarse model makes reference events repeat: many exact ties in the matrix
+        lm = (np.round(lm / 8.0) * 8.0).astype(np.float32)
+    ctx = capi.Context(lm, k, flags=capi.SFGPU_SAM, query_size=q, prefix_size=20)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    paths, ev_start, ev_len = ctx.collect_paths(0, got)
+    ref = H.OracleRef(seqs, lm, k, 0, q)
+    O = H.oracle()
+    for i, (s, cc) in enumerate(zip(sigs, sc)):
+        o = H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], 0, q, 20)
+        assert_hit_equal(got[i], o, ("path", q, quant, i), 0, q, 20)
+        ev = H.orc_events(s, cc["digitisation"], cc["offset"], cc["range"], False)
+        lo, hi = o.qstart, o.qend
+        assert np.array_equal(ev_start[i][:hi - lo], ev["start"][lo:hi])
+        assert np.array_equal(bits(ev_len[i][:hi - lo]), bits(ev["length"][lo:hi]))
+        x = ctx.query(0, i)
+        y = ref.fwd(o.rid) if o.strand == b"+" else ref.rev(o.rid)
+        n, m = len(x), len(y)
+        cost = np.zeros(n * m, dtype=np.float32)
+        O.orc_subsequence(x, y, n, m, cost)
+        px = np.zeros(n + m, dtype=np.int32)
+        py = np.zeros(n + m, dtype=np.int32)
+        kk = O.orc_path_full(cost, n, m, o.raw_pos_end, px, py)
+        assert paths[i] is not None
+        assert np.array_equal(paths[i][0], px[:kk]) and np.array_equal(paths[i][1], py[:kk]), (q, quant, i)
+    ref.close()
+    ctx.close()
