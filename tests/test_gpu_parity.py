@@ -352,3 +352,37 @@ def test_warping_paths_match_oracle_backtrack(q, quant):
         assert np.array_equal(paths[i][0], px[:kk]) and np.array_equal(paths[i][1], py[:kk]), (q, quant, i)
     ref.close()
     ctx.close()
+
+
+def test_c4_shaped_sample_truth_and_oracle_parity():
+    """BASELINE.json configs[3] shape (R10 k=9, one 1 Mb contig, both strands, production checkpoint spacing):
+    synthetic reads must come back at their true locus (the reference's own 85 % gate), the batch result must
+    not depend on batch composition, and a few reads are checked field by field against the CPU oracle
+    (3.4 s of CPU each: 2 x 250 x 999 992 cells)."""
+    k = 9
+    lm = model(k)
+    rng = np.random.default_rng(1)
+    seq = synth.random_sequence(1_000_000, rng)
+    sigs, truth = synth.simulate_reads([seq], k, lm, 192, seed=77, bases_per_read=450)
+    sc = [synth.DNA_SCALING] * len(sigs)
+    ctx = capi.Context(lm, k)
+    ctx.set_ref([seq])
+    got = ctx.map_batch(sigs, sc)
+    ok = 0
+    for g, (ci, strand, st) in zip(got, truth):
+        assert g["qlen"] == 250 and g["rid"] == 0
+        # truth and the raw result are both in the coordinates of the strand's own event array;
+        # the query starts ~50 events (~bases) into the read
+        near = abs(int(g["pos_st"]) - (st + 50)) < 100  # the tolerance of the reference's own `eval`
+        ok += int("+-"[g["strand"]] == strand and near)
+    assert ok >= 0.85 * len(sigs), ok  # the reference's accuracy gate for DNA (test/test.sh:54-55)
+    # same reads, different batch split / slot: identical records
+    a = ctx.map_batch(sigs[:50], sc[:50], slot=1)
+    b = ctx.map_batch(sigs[50:], sc[50:], slot=0)
+    assert np.concatenate([a, b]).tobytes() == got.tobytes()
+    ref = H.OracleRef([seq], lm, k, 0, 250)
+    for i in (0, 7, 101):
+        o = H.orc_map(ref, sigs[i], 8192.0, 10.0, 1402.882, 0, 250, 50)
+        assert_hit_equal(got[i], o, ("c4", i), 0, 250, 50)
+    ref.close()
+    ctx.close()
