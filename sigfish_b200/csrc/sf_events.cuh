@@ -11,25 +11,28 @@
 // The MAD trim of events.c:99-269 has no effect on the reference's results (its return value is
 // dropped at events.c:567) and is not implemented.
 //
-// One read per block.  The signal is consumed in tiles of SF_EV_TILE samples:
-//   1. every thread loads 8 consecutive int16 samples with one 16-byte load and converts to pA;
-//   2. block-wide fp64 scan of (x, x*x) continuing from the previous tile.  Every addition is
+// One read per WARP (the sequential peak detector is the critical path of a read, so the way to go faster
+// is more reads in flight per SM, not more threads per read).  The signal is consumed in tiles of
+// SF_EV_TILE samples:
+//   1. every lane loads 8 consecutive int16 samples with one 16-byte load and converts to pA;
+//   2. warp-wide fp64 scan of (x, x*x) continuing from the previous tile.  Every addition is
 //      checked with TwoSum: when all partial sums are exact the scan equals the reference's
 //      sequential sums bit for bit; a tile with any inexact addition is redone sequentially by
 //      one thread in the reference's order;
-//   3. every thread computes both t-statistics for its positions (32 samples behind the scan so
+//   3. every lane computes both t-statistics for its positions (32 samples behind the scan so
 //      that the right-hand window is available);
-//   4. one thread runs the two coupled peak finders over the tile (inherently sequential),
-//      closes events as boundaries are emitted and stops the block as soon as the query window
-//      is complete (exact: the detector is causal).
+//   4. lane 0 runs the two coupled peak finders over the tile (inherently sequential), closes
+//      events as boundaries are emitted and stops the warp as soon as the query window is
+//      complete (exact: the detector is causal).
 #pragma once
 #include <cuda_runtime.h>
 #include <cfloat>
 #include "sf_types.cuh"
 
-#define SF_EV_THREADS 128
+#define SF_EV_READS_PER_BLOCK 4
+#define SF_EV_THREADS (32 * SF_EV_READS_PER_BLOCK)
 #define SF_EV_PER_THREAD 8
-#define SF_EV_TILE (SF_EV_THREADS * SF_EV_PER_THREAD) // 1024 samples
+#define SF_EV_TILE (32 * SF_EV_PER_THREAD)           // 256 samples per warp per tile
 #define SF_EV_LAG 32                                  // t-stat runs this far behind the scan
 #define SF_EV_KEEP 64                                 // prefix sums kept from the previous tile
 
@@ -115,17 +118,20 @@ __device__ __forceinline__ void sf_twosum(double a, double b, double &s, int &in
 
 __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_args a)
 {
-    // prefix sums of the samples [rel, rel + KEEP + TILE]; slot j holds S[rel + j]
-    __shared__ double S[SF_EV_KEEP + SF_EV_TILE + 1];
-    __shared__ double SS[SF_EV_KEEP + SF_EV_TILE + 1];
-    __shared__ float T1[SF_EV_TILE + SF_EV_LAG];
-    __shared__ float T2[SF_EV_TILE + SF_EV_LAG];
-    __shared__ double wsum[SF_EV_THREADS / 32], wsq[SF_EV_THREADS / 32];
-    __shared__ int stop_flag;
+    // per warp: prefix sums of the samples [rel, rel + KEEP + TILE]; slot j holds S[rel + j]
+    __shared__ double S_all[SF_EV_READS_PER_BLOCK][SF_EV_KEEP + SF_EV_TILE + 1];
+    __shared__ double SS_all[SF_EV_READS_PER_BLOCK][SF_EV_KEEP + SF_EV_TILE + 1];
+    __shared__ float T1_all[SF_EV_READS_PER_BLOCK][SF_EV_TILE + SF_EV_LAG];
+    __shared__ float T2_all[SF_EV_READS_PER_BLOCK][SF_EV_TILE + SF_EV_LAG];
 
-    const int read = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x & 31; // lane: the warp is the unit of work
+    const int read = blockIdx.x * SF_EV_READS_PER_BLOCK + warp;
+    if (read >= a.n_reads)
+        return;
+    double *S = S_all[warp], *SS = SS_all[warp];
+    float *T1 = T1_all[warp], *T2 = T2_all[warp];
     const long long n = a.sig_len[read];
     const int16_t *raw = a.signal + a.sig_off[read];
     const bool rna = (a.flags & SF_RNA) != 0;
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
     uint64_t *ev_start = a.ev_start + (size_t)read * cap;
     float *ev_mean = a.ev_mean + (size_t)read * cap;
     float *ev_len = a.ev_len + (size_t)read * cap;
-    // events needed before the block may stop: boundary index qend-1 must exist
+    // events needed before the warp may stop: boundary index qend-1 must exist
     const bool autop = a.p < 0 && !a.keep_all;
     const long long pe = autop ? a.polya_end[read] : -1; // sigfish.c:380-422
     long long need_peaks = (from_end || a.keep_all) ? (1ll << 62) : (long long)(a.p < 0 ? 50 : a.p) + a.q;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         need_peaks = 1ll << 62; // until the first event at or after the poly-A end is known
     long long qs = -1;          // index of that event
 
-    // sequential state (thread 0 only)
+    // sequential state (lane 0 only)
     sf_finder f0, f1;
     f0.threshold = rna ? 2.5f : 1.4f; f1.threshold = 9.0f;
     f0.window = w1; f1.window = w2;
@@ -157,12 +163,12 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
     unsigned long long prev_b = 0; // start of the open event
     double prev_s = 0.0;           // prefix sum there
     int sticky = 0;
+    int stop_flag = 0;
 
     if (tid == 0) {
-        stop_flag = 0;
         S[SF_EV_KEEP] = 0.0; SS[SF_EV_KEEP] = 0.0; // S[0] for the first tile (rel = -KEEP)
     }
-    __syncthreads();
+    __syncwarp();
 
     if (n <= 0) {
         if (tid == 0) {
@@ -203,29 +209,24 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                 ps[k] = acc; pq[k] = acq;
             }
         }
-        // warp-inclusive scan of the thread totals
+        // warp-inclusive scan of the lane totals
         double tot = ps[SF_EV_PER_THREAD - 1], toq = pq[SF_EV_PER_THREAD - 1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const double us = __shfl_up_sync(0xffffffffu, tot, o);
-            const double uq = __shfl_up_sync(0xffffffffu, toq, o);
-            if (lane >= o) {
+            const double us = __shfl_up_sync(full, tot, o);
+            const double uq = __shfl_up_sync(full, toq, o);
+            if (tid >= o) {
                 sf_twosum(tot, us, tot, inexact);
                 sf_twosum(toq, uq, toq, inexact);
             }
         }
-        if (lane == 31) { wsum[warp] = tot; wsq[warp] = toq; }
-        __syncthreads();
         double carry = S[SF_EV_KEEP], carq = SS[SF_EV_KEEP]; // prefix sum at `base`
-        for (int wv = 0; wv < warp; wv++) {
-            sf_twosum(carry, wsum[wv], carry, inexact);
-            sf_twosum(carq, wsq[wv], carq, inexact);
-        }
-        // exclusive prefix of this thread = carry + (tot - own total) -> take it from the lane below
-        double exs = __shfl_up_sync(0xffffffffu, tot, 1), exq = __shfl_up_sync(0xffffffffu, toq, 1);
-        if (lane == 0) { exs = 0.0; exq = 0.0; }
+        // exclusive prefix of this lane = carry + total of the lanes below
+        double exs = __shfl_up_sync(full, tot, 1), exq = __shfl_up_sync(full, toq, 1);
+        if (tid == 0) { exs = 0.0; exq = 0.0; }
         sf_twosum(carry, exs, carry, inexact);
         sf_twosum(carq, exq, carq, inexact);
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < SF_EV_PER_THREAD; k++) {
             double vs, vq;
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
             const int slot = SF_EV_KEEP + 1 + tid * SF_EV_PER_THREAD + k;
             S[slot] = vs; SS[slot] = vq;
         }
-        const int any_inexact = __syncthreads_or(inexact);
+        const int any_inexact = __any_sync(full, inexact);
+        __syncwarp();
         if (any_inexact) {
             // redo this tile in the reference's order (events.c:303-306); needs the pA values again
             if (tid == 0) {
@@ -248,22 +250,22 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                 }
                 sticky = 1;
             }
-            __syncthreads();
+            __syncwarp();
         }
 
         // ---- 3: t-statistics for positions [base - LAG, hi_pos) ----
         const long long scanned = min(base + SF_EV_TILE, n); // prefix sums known up to S[scanned]
         const long long lo_pos = base - SF_EV_LAG < 0 ? 0 : base - SF_EV_LAG;
         const long long hi_pos = (scanned >= n) ? n : base + SF_EV_TILE - SF_EV_LAG;
-        for (long long i = lo_pos + tid; i < hi_pos; i += SF_EV_THREADS) {
+        for (long long i = lo_pos + tid; i < hi_pos; i += 32) {
             float t1 = 0.0f, t2 = 0.0f;
             if (n >= 2 * w1 && i >= w1 && i <= n - w1) t1 = sf_tstat_at(S, SS, i, w1, rel);
             if (n >= 2 * w2 && i >= w2 && i <= n - w2) t2 = sf_tstat_at(S, SS, i, w2, rel);
             T1[i - lo_pos] = t1; T2[i - lo_pos] = t2;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- 4: sequential peak finders + event closing (thread 0) ----
+        // ---- 4: sequential peak finders + event closing (lane 0) ----
         if (tid == 0) {
             for (long long i = lo_pos; i < hi_pos; i++) {
 #pragma unroll
@@ -326,15 +328,24 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                 }
             }
         }
-        // keep the last KEEP+1 prefix sums for the next tile
-        __syncthreads();
+        stop_flag = __shfl_sync(full, stop_flag, 0);
         if (stop_flag)
             break;
-        double ks = 0.0, kq = 0.0;
-        if (tid <= SF_EV_KEEP) { ks = S[SF_EV_TILE + tid]; kq = SS[SF_EV_TILE + tid]; }
-        __syncthreads();
-        if (tid <= SF_EV_KEEP) { S[tid] = ks; SS[tid] = kq; }
-        __syncthreads();
+        // keep the last KEEP+1 prefix sums for the next tile
+        double ks[3], kq[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const int idx = tid + 32 * e;
+            ks[e] = idx <= SF_EV_KEEP ? S[SF_EV_TILE + idx] : 0.0;
+            kq[e] = idx <= SF_EV_KEEP ? SS[SF_EV_TILE + idx] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const int idx = tid + 32 * e;
+            if (idx <= SF_EV_KEEP) { S[idx] = ks[e]; SS[idx] = kq[e]; }
+        }
+        __syncwarp();
     }
 
     // ---- window + z-score + query (thread 0; fp32 sums in the reference's order) ----

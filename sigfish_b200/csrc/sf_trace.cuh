@@ -173,37 +173,56 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
         const int tl = trow / R, tr = trow % R;
         const int t_end = tpos + tl; // step at which the target cell is produced
         int sres = 0;
-        for (int t = t0; t <= t_end; t++) {
-            const int pos = t - lane;
-            const float yy = (pos >= 0 && pos < n_pos) ? __ldg(y + pos) : SF_INF;
-            float up = __shfl_up_sync(full, bot, 1);
-            int sup = __shfl_up_sync(full, sbot, 1);
-            if (lane == 0) {
-                up = STD ? (yy == SF_INF ? 0.0f : SF_INF) : 0.0f;
-                sup = 0;
-            }
-            const float unext = up;
-            const int sunext = sup;
-            float dg = dprev;
-            int sdg = sdprev;
+        // reference events are fetched 32 steps at a time (one coalesced load per lane) and handed to the
+        // lanes by shuffle: lane l needs position t - l, which sits in this block's or the previous block's load
+        float yprev;
+        {
+            const int pp = t0 - 32 + lane;
+            yprev = (pp >= 0 && pp < n_pos) ? __ldg(y + pp) : SF_INF;
+        }
+        const int n_blk = (t_end - t0) / 32 + 1;
+        for (int blk = 0; blk < n_blk; blk++) {
+            const int tb = t0 + 32 * blk;
+            const int pc = tb + lane;
+            const float ycur = (pc >= 0 && pc < n_pos) ? __ldg(y + pc) : SF_INF;
+#pragma unroll 4
+            for (int s32 = 0; s32 < 32; s32++) {
+                const int t = tb + s32;
+                const int pos = t - lane;
+                const int src = (s32 - lane) & 31;
+                const float ya = __shfl_sync(full, ycur, src);
+                const float yb = __shfl_sync(full, yprev, src);
+                const float yy = s32 >= lane ? ya : yb;
+                float up = __shfl_up_sync(full, bot, 1);
+                int sup = __shfl_up_sync(full, sbot, 1);
+                if (lane == 0) {
+                    up = STD ? (yy == SF_INF ? 0.0f : SF_INF) : 0.0f;
+                    sup = 0;
+                }
+                const float unext = up;
+                const int sunext = sup;
+                float dg = dprev;
+                int sdg = sdprev;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const float m = fminf(fminf(up, dg), L[r]);
-                int s = (dg == m) ? sdg : ((L[r] == m) ? S[r] : sup);
-                if (lane == 0 && r == 0)
-                    s = pos - seg_lo; // start(0, j) = j
-                const float nv = fabsf(x[r] - yy) + m;
-                dg = L[r]; sdg = S[r];
-                L[r] = nv; S[r] = s;
-                up = nv; sup = s;
-            }
-            dprev = unext; sdprev = sunext;
-            bot = L[R - 1]; sbot = S[R - 1];
-            if (t == t_end) {
+                for (int r = 0; r < R; r++) {
+                    const float m = fminf(fminf(up, dg), L[r]);
+                    int s = (dg == m) ? sdg : ((L[r] == m) ? S[r] : sup);
+                    if (lane == 0 && r == 0)
+                        s = pos - seg_lo; // start(0, j) = j
+                    const float nv = fabsf(x[r] - yy) + m;
+                    dg = L[r]; sdg = S[r];
+                    L[r] = nv; S[r] = s;
+                    up = nv; sup = s;
+                }
+                dprev = unext; sdprev = sunext;
+                bot = L[R - 1]; sbot = S[R - 1];
+                if (t == t_end) {
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (r == tr) sres = S[r];
+                    for (int r = 0; r < R; r++)
+                        if (r == tr) sres = S[r];
+                }
             }
+            yprev = ycur;
         }
         sres = __shfl_sync(full, sres, tl);
         if (sres >= 0 || k < 0) {

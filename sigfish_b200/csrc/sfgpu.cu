@@ -87,7 +87,7 @@ struct sfgpu_ctx {
     int32_t *d_order = nullptr, *d_seg_group = nullptr;
     int64_t ck_per_read = 0, ref_columns = 0;
     int32_t min_window = 0;
-    int32_t ck_min_cols = 8192; // segments longer than this get wavefront checkpoints (reserved[0] overrides)
+    int32_t ck_min_cols = 2048; // segments longer than this get wavefront checkpoints (reserved[0] overrides)
     std::vector<sf_slot> slots;
     int dtw_blocks_per_sm = 0;
     char err[512];
@@ -300,7 +300,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
         }
-        sf_events_kernel<<<n, SF_EV_THREADS, 0, st>>>(ea);
+        sf_events_kernel<<<(n + SF_EV_READS_PER_BLOCK - 1) / SF_EV_READS_PER_BLOCK, SF_EV_THREADS, 0, st>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         s.timing.other_launches++;
     }
@@ -464,8 +464,8 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
         if (g.end - g.begin > 0x7ffffff0ll)
             return fail(c, SFGPU_ELIMIT, "segment group too long");
         if (longest > c->ck_min_cols) {
-            // checkpoint period: ~1/512 of the segment, clamped
-            const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, std::min<int64_t>(8192, longest / 512));
+            // checkpoint period: ~1/256 of the segment, between ck_min_cols/4 (512) and 4096 columns
+            const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, std::min<int64_t>(4096, longest / 256));
             g.ck_every = (int32_t)((cols_per + 31) / 32);
             g.n_ck = (int32_t)(((g.end - g.begin) / 32) / g.ck_every);
         }
