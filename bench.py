@@ -41,12 +41,12 @@ KMER = 9
 Q, P = 250, 50
 WORKLOAD = "C4: synthetic R10 DNA (k=9), reads x q=250 vs one 1 Mb contig, both strands"
 
-# The DTW inner loop issues 28 SASS instructions per warp for one step of 32 lanes x R=8 rows (cuobjdump of
-# sf_dtw_score_kernel<8,false>: 16 FADD + 8 FMNMX3 + LDS + SHFL + IMAD + STS).  FMNMX3 runs on the half-rate
-# ALU pipe and blocks the issue port for 2 cycles (measured: tools/ubench_alu.cu, profiles/r01_ubench_alu.txt),
-# so a step costs 28 + 8 = 36 issue slots.  See DESIGN.md "Roofline".
-SASS_PER_STEP = 28.0
-ISSUE_SLOTS_PER_STEP = 36.0
+# The DTW inner loop issues 54 SASS instructions per warp for one macro-step of 32 lanes x R=8 rows x 2 columns
+# (cuobjdump of sf_dtw_score_kernel<8,false>: 32 FADD + 16 FMNMX3 + LDS.64 + 2 SHFL + 2 IMAD + STS.64), i.e. 27 per
+# column of 256 cells.  FMNMX3 runs on the half-rate ALU pipe and blocks the issue port for 2 cycles (measured:
+# tools/ubench_alu.cu, profiles/r01_ubench_alu.txt), so a column costs 27 + 8 = 35 issue slots.  DESIGN.md 5.1.
+SASS_PER_STEP = 27.0
+ISSUE_SLOTS_PER_STEP = 35.0
 ROWS_PER_LANE = 8
 
 
@@ -179,7 +179,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=4096, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=0,
+                    help="reads per GPU per step (0: two full waves of DTW tasks, sfgpu_wave_reads(); 5920 on a 148-SM B200)")
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU baseline sample (0: one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -201,11 +202,15 @@ def main():
     R = ranks.Ranks(backend="nccl", device=torch.device("cuda", local))
     barrier = R.barrier
 
-    mean, stdv, seq, sigs = make_workload(args.reads, seed=100 + rank, ref_len=args.ref_len)
     from sigfish_b200 import synth
-    sc = [synth.DNA_SCALING] * len(sigs)
+    mean, stdv = synth.make_model(KMER)
+    seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
     ctx = capi.Context(mean, KMER, flags=0, query_size=Q, prefix_size=P, device=local, n_slots=2)
     ctx.set_ref([seq])
+    # a task (one read x one strand of the 1 Mb contig) runs ~150 ms, so the batch is sized to whole waves
+    n_reads = args.reads if args.reads > 0 else 2 * ctx.wave_reads
+    sigs, _ = synth.simulate_reads([seq], KMER, mean, n_reads, seed=100 + rank, bases_per_read=450)
+    sc = [synth.DNA_SCALING] * len(sigs)
     packed = ctx.pack(sigs, sc)
     ref_cols = ctx.ref_columns
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -280,6 +285,7 @@ def main():
             "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": len(sigs), "query_size": Q, "prefix_size": P,
                        "kmer": KMER, "ref_columns": int(ref_cols), "cells_per_step_per_gpu": cells,
                        "samples_per_step_per_gpu": int(sum(len(s) for s in sigs)), "mapped_reads": mapped,
+                       "batch": "two full waves of (read, strand) DTW tasks per step (sfgpu_wave_reads)" if args.reads <= 0 else "--reads",
                        "l2": "256 MB buffer written between timed iterations (L2 flush)",
                        "parallelism": f"reads sharded over {world} GPU(s), reference replicated, no collective"},
             "stage_ms": {"events": evt_ms, "dtw": dtw_ms, "merge_trace": trc_ms, "wall_per_step_incl_flush": wall_step},
@@ -292,7 +298,7 @@ def main():
                          "frac": dtw_cells_per_s / peak_cells, "traffic": None,
                          "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
                                         f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
-                                        f"({SASS_PER_STEP:.0f} SASS, the 8 half-rate FMNMX3 counted twice)",
+                                        f"({SASS_PER_STEP:.0f} SASS per column, the 8 half-rate FMNMX3 counted twice)",
                          "frac_if_every_sass_were_one_slot": dtw_cells_per_s / peak_naive,
                          "events_kernel_GBps": (job_samples / world) * 2 / (evt_ms * 1e-3) / 1e9 if evt_ms > 0 else None,
                          "hbm_peak_GBps": peaks.get("hbm_gbs")},

@@ -17,7 +17,7 @@ SFGPU_RNA, SFGPU_DTW, SFGPU_INV, SFGPU_REF, SFGPU_END, SFGPU_SAM = 0x001, 0x002,
 SYMBOLS = ["sfgpu_device_count", "sfgpu_create", "sfgpu_set_ref", "sfgpu_submit", "sfgpu_resubmit",
            "sfgpu_collect", "sfgpu_timing", "sfgpu_destroy", "sfgpu_strerror", "sfgpu_ref_events",
            "sfgpu_event_table", "sfgpu_query", "sfgpu_ref_columns", "sfgpu_set_ref_events",
-           "sfgpu_submit_queries", "sfgpu_collect_paths"]
+           "sfgpu_submit_queries", "sfgpu_collect_paths", "sfgpu_wave_reads"]
 
 
 class Opt(C.Structure):
@@ -78,6 +78,8 @@ def lib():
     L.sfgpu_collect_paths.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_ref_columns.argtypes = [vp]
     L.sfgpu_ref_columns.restype = C.c_int64
+    L.sfgpu_wave_reads.argtypes = [vp]
+    L.sfgpu_wave_reads.restype = C.c_int32
     _lib = L
     return L
 
@@ -245,6 +247,10 @@ class Context:
         out = np.zeros(self.opt.query_size, dtype=np.float32)
         n = self._check(lib().sfgpu_query(self._h, slot, read, _ptr(out), out.shape[0]), "sfgpu_query")
         return out[:n]
+
+    @property
+    def wave_reads(self) -> int:
+        return lib().sfgpu_wave_reads(self._h)
 
     @property
     def ref_columns(self) -> int:

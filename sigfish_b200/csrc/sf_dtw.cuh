@@ -9,11 +9,14 @@
 //   src/sigfish.c:575-596 update_aln()         -- insertion list; of equal scores the later wins
 //
 // Mapping to the hardware: one warp owns one (read, segment group) task.  Lane l keeps query rows
-// [l*R, (l+1)*R) of the current DTW column in registers (R = ceil(q/32)); at step t lane l works
-// on stream column t - l, so the anti-diagonal dependency is one __shfl_up_sync per step.  The
-// reference events reach the lanes through a 128-float mirrored ring in shared memory (one
-// coalesced global load per 32 steps per warp, one LDS per step per lane).  No cost matrix
-// exists anywhere: the state is O(qlen) registers per warp.
+// [l*R, (l+1)*R) of the DTW column in registers (R = ceil(q/32)).  A *macro-step* advances every lane
+// by TWO reference columns: at macro-step T lane l computes columns 2(T-l) and 2(T-l)+1 of its rows.
+// The second column of a row only needs the first column of the same row, so the two columns form two
+// interleaved dependency chains (critical path R+1 cells for 2R cells: ILP 2 inside one warp), and
+// the per-column overheads are shared: one 8-byte LDS for both reference events, one 8-byte STS of the
+// last query row, two shuffles for the two bottom-row hand-offs to the next lane.  The reference
+// events reach the lanes through a ring of float2 pairs in shared memory (one coalesced global load
+// per 32 macro-steps).  No cost matrix exists anywhere: the state is O(qlen) registers per warp.
 //
 // Arithmetic per cell (bit-exact with the CPU, -fmad=false):
 //     t  = x_i - y_j                (FADD)
@@ -28,7 +31,8 @@
 
 #define SF_DTW_WARPS 4
 #define SF_DTW_THREADS (SF_DTW_WARPS * 32)
-#define SF_RING 128
+#define SF_RING_PAIRS 128 // float2 slots: two blocks of 32 pairs, stored twice (mirror) for wrap-free reads
+#define SF_BLOCK_COLS 64  // reference columns per block of 32 macro-steps
 
 struct sf_dtw_args {
     const float *stream;
@@ -41,94 +45,115 @@ struct sf_dtw_args {
     const sf_readinfo *info;
     int32_t q_cap;
     sf_taskres *res;        // [n_reads][n_groups]
-    float *ckpt;            // [(read * ck_per_read + ck_prefix + k)][R+1][32]
+    float *ckpt;            // [(read * ck_per_read + ck_prefix + k)][R+2][32]
     int64_t ck_per_read;
     unsigned int *counter;
 };
 
-__host__ __device__ inline int sf_smem_floats_per_warp(int R) { return SF_RING + 32 * R; }
+// ring (float2 x 128) + last-row buffer (2 values per macro-step; 2R in the generic block)
+__host__ __device__ inline int sf_smem_floats_per_warp(int R) { return 2 * SF_RING_PAIRS + 64 * R; }
+// one wavefront checkpoint: L[R], dprev, botA per lane
+__host__ __device__ inline int sf_ckpt_floats(int R) { return (R + 2) * 32; }
 
-// register of the last query row for which the 32-step block is specialised (the generic block
-// stores all R registers of the last-row lane; the specialised one stores just this one): the
-// common full-length queries of the default -q values (250, 500, 100) and q = multiples of R
+// register of the last query row for which the block is specialised (the generic block stores all
+// R registers of the last-row lane; the specialised one stores just this one): the common full-length
+// queries of the default -q values (250, 500, 100) and q = multiples of R
 __host__ __device__ constexpr int sf_fast_rq(int R) { return R == 8 ? 1 : (R == 16 ? 3 : (R == 4 ? 3 : R - 1)); }
 
-__host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 8 : (R <= 16 ? 6 : (R <= 24 ? 4 : 3))); }
+__host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 7 : (R <= 16 ? 5 : (R <= 24 ? 4 : 3))); }
 
 // Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses whose base is made
-// opaque once per block of 32 steps: otherwise the compiler re-derives the ring / buffer address from
-// its parts on every step (3-4 extra integer instructions per step) to save two registers.
+// opaque once per block: otherwise the compiler re-derives the ring / buffer address from its parts on
+// every step (3-4 extra integer instructions per step) to save two registers.
 __device__ __forceinline__ unsigned sf_smem_addr(const void *p)
 {
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("" : "+r"(a));
     return a;
 }
-__device__ __forceinline__ float sf_lds(unsigned addr)
+__device__ __forceinline__ float2 sf_lds2(unsigned addr)
 {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sf_sts(unsigned addr, float v)
+__device__ __forceinline__ void sf_sts2(unsigned addr, float a, float b)
 {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b));
 }
 __device__ __forceinline__ void sf_sts4(unsigned addr, float a, float b, float c, float d)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
+// lane 0 is fed +0 (virtual row -1); an integer multiply by 0/1 keeps this off the half-rate ALU pipe
+__device__ __forceinline__ float sf_mask0(float v, int nz)
+{
+    int ub;
+    asm("mul.lo.s32 %0, %1, %2;" : "=r"(ub) : "r"(__float_as_int(v)), "r"(nz)); // IMAD: fma pipe
+    return __int_as_float(ub);
+}
 
-// 32 wavefront steps.  RQ >= 0: the last query row sits in register RQ of lane lq and only that value
-// is handed to the chunk scan (last[s]); RQ < 0: all R registers are stored (last[s*R + r]).
+// 32 macro-steps = 64 reference columns.  RQ >= 0: the last query row sits in register RQ of lane lq and
+// only its two values are handed to the chunk scan (last[2s], last[2s+1]); RQ < 0: all R registers of
+// both columns are stored (last[(s*R + r)*2 + c]).
+// State between macro-steps: L[r] = row r at the lane's second column, botA/botB = bottom row at the
+// lane's two columns (read by the next lane one macro-step later), dprev = the `up` input of the second
+// column (the diagonal of row 0 at the next macro-step's first column).
 template <int R, bool STD, int RQ>
-__device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R], float &bot, float &dprev,
-                                             const float *yb, float *last, const bool is_lq, const int lane,
-                                             const int nz)
+__device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R], float &botA, float &botB,
+                                             float &dprev, const float2 *yb, float *last, const bool is_lq,
+                                             const int lane, const int nz)
 {
     const unsigned full = 0xffffffffu;
     const unsigned yb_s = sf_smem_addr(yb);
     const unsigned last_s = sf_smem_addr(last);
 #pragma unroll
     for (int s = 0; s < 32; s++) {
-        const float yy = sf_lds(yb_s + 4 * s);
-        float up = __shfl_up_sync(full, bot, 1);
+        const float2 yy = sf_lds2(yb_s + 8 * s);
+        float upA = __shfl_up_sync(full, botA, 1);
+        float upB = __shfl_up_sync(full, botB, 1);
         if (STD) {
-            if (lane == 0)
-                up = yy == SF_INF ? 0.0f : SF_INF;
+            if (lane == 0) {
+                upA = yy.x == SF_INF ? 0.0f : SF_INF;
+                upB = yy.y == SF_INF ? 0.0f : SF_INF;
+            }
         } else {
-            // lane 0 is fed +0 (virtual row -1); integer multiply keeps this off the half-rate ALU pipe
-            int ub;
-            asm("mul.lo.s32 %0, %1, %2;" : "=r"(ub) : "r"(__float_as_int(up)), "r"(nz)); // IMAD: fma pipe
-            up = __int_as_float(ub);
+            upA = sf_mask0(upA, nz);
+            upB = sf_mask0(upB, nz);
         }
-        const float unext = up;
-        float dg = dprev;
-        float t[R];
-#pragma unroll
-        for (int r = 0; r < R; r++)
-            t[r] = x[r] - yy;
+        const float next_dprev = upB;
+        float dgA = dprev, dgB = upA;
+        float keepA = 0.0f, keepB = 0.0f;
+        float allA[RQ < 0 ? R : 1];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float m = fminf(fminf(up, dg), L[r]);
-            const float nv = fabsf(t[r]) + m;
-            dg = L[r];
-            L[r] = nv;
-            up = nv;
+            const float tA = x[r] - yy.x;
+            const float tB = x[r] - yy.y;
+            const float a = fabsf(tA) + fminf(fminf(upA, dgA), L[r]);
+            const float b = fabsf(tB) + fminf(fminf(upB, dgB), a);
+            dgA = L[r];
+            dgB = a;
+            L[r] = b;
+            upA = a;
+            upB = b;
+            if (RQ >= 0) {
+                if (r == RQ) { keepA = a; keepB = b; }
+            } else {
+                allA[r] = a;
+            }
         }
-        dprev = unext;
-        bot = L[R - 1];
+        dprev = next_dprev;
+        botA = upA;
+        botB = upB;
         if (is_lq) {
             if (RQ >= 0) {
-                sf_sts(last_s + 4 * s, L[RQ]);
-            } else if (R % 4 == 0) {
-#pragma unroll
-                for (int r = 0; r < R; r += 4)
-                    sf_sts4(last_s + 4 * (s * R + r), L[r], L[r + 1], L[r + 2], L[r + 3]);
+                sf_sts2(last_s + 8 * s, keepA, keepB);
             } else {
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    sf_sts(last_s + 4 * (s * R + r), L[r]);
+                for (int r = 0; r + 1 < R; r += 2)
+                    sf_sts4(last_s + 8 * (s * R + r), allA[r], L[r], allA[r + 1], L[r + 1]);
+                if (R & 1)
+                    sf_sts2(last_s + 8 * (s * R + R - 1), allA[R - 1], L[R - 1]);
             }
         }
     }
@@ -137,11 +162,11 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
 template <int R, bool STD>
 __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_score_kernel(const sf_dtw_args a)
 {
-    extern __shared__ float sf_smem[];
+    extern __shared__ float2 sf_smem2[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *ring = sf_smem + warp * sf_smem_floats_per_warp(R);
-    float *last = ring + SF_RING;
+    float2 *ring = sf_smem2 + warp * (sf_smem_floats_per_warp(R) / 2);
+    float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
     const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)a.n_reads;
 
@@ -179,18 +204,23 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
             x[r] = row < qlen ? q[row] : 0.0f;
             L[r] = SF_INF;
         }
-        float bot = SF_INF;
+        float botA = SF_INF, botB = SF_INF;
         float dprev = (lane == 0 && !STD) ? 0.0f : SF_INF;
 
         const float *y = a.stream + grp.begin;
         const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
-        const int n_blocks = (n_pos + lq + 31) >> 5;
+        // the last column (n_pos-1) is in pair (n_pos-1)/2 and reaches lane lq lq macro-steps later
+        const int n_blocks = ((n_pos - 1) / 2 + lq + 32) >> 5;
 
-        // ring: block b lives at slots (b&1)*32 + j and again 64 slots later
+        __syncwarp();
+        // ring: block b (pairs 32b .. 32b+31) lives at slots (b&1)*32 + j and again 64 slots later;
+        // the block "before" block 0 reads as +INF columns
         {
-            const float y0 = lane < n_pos ? y[lane] : SF_INF;
-            ring[lane] = y0; ring[64 + lane] = y0;
-            ring[32 + lane] = SF_INF; ring[96 + lane] = SF_INF;
+            const int c0 = 2 * lane, c1 = c0 + 1;
+            const float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
+            ring[lane] = v; ring[64 + lane] = v;
+            const float2 inf2 = make_float2(SF_INF, SF_INF);
+            ring[32 + lane] = inf2; ring[96 + lane] = inf2;
         }
         __syncwarp();
 
@@ -209,28 +239,41 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
         int ck = 0;
 
         for (int b = 0; b < n_blocks; b++) {
-            // prefetch the next 32 reference events; consumed after the 32 steps below
-            const int nidx = 32 * (b + 1) + lane;
-            const float ynext = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
-            const float *yb = ring + ((b & 1) ? 32 : 64) - lane;
+            // prefetch the next 64 reference events; published after the 32 macro-steps below
+            const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
+            const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
+            const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
+            const float2 *yb = ring + ((b & 1) ? 32 : 64) - lane;
 
             if (fast)
-                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, bot, dprev, yb, last, is_lq, lane, nz);
+                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, lane, nz);
             else
-                sf_dtw_block<R, STD, -1>(x, L, bot, dprev, yb, last, is_lq, lane, nz);
+                sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, lane, nz);
             __syncwarp();
 
-            // ---- last-row chunk minima (sigfish.c:891-901) ----
+            // ---- last-row chunk minima (sigfish.c:891-901): this block produced the last row of columns
+            //      p0 .. p0+63; lane l looks at p0+2l and p0+2l+1 ----
             {
-                const int p0 = 32 * b - lq;
-                const int pos = p0 + lane;
-                const float v = fast ? last[lane] : last[lane * R + rq];
+                const int p0 = SF_BLOCK_COLS * b - 2 * lq;
+                const int pos0 = p0 + 2 * lane;
+                float v0, v1;
+                if (fast) {
+                    const float2 v = *reinterpret_cast<const float2 *>(last + 2 * lane);
+                    v0 = v.x; v1 = v.y;
+                } else {
+                    const float2 v = *reinterpret_cast<const float2 *>(last + (lane * R + rq) * 2);
+                    v0 = v.x; v1 = v.y;
+                }
                 for (;;) {
-                    if (pos >= clo && pos < chi && v < rmin) {
-                        rmin = v;
-                        rpos = pos;
+                    if (pos0 >= clo && pos0 < chi && v0 < rmin) {
+                        rmin = v0;
+                        rpos = pos0;
                     }
-                    if (chi > p0 + 32)
+                    if (pos0 + 1 >= clo && pos0 + 1 < chi && v1 < rmin) {
+                        rmin = v1;
+                        rpos = pos0 + 1;
+                    }
+                    if (chi > p0 + SF_BLOCK_COLS)
                         break;
                     // chunk complete: first strict minimum = smallest value, then smallest column
                     float m = rmin;
@@ -273,19 +316,21 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 
             // ---- checkpoint of the skewed wavefront (for the start-coordinate pass) ----
             if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)((R + 1) * 32);
+                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)sf_ckpt_floats(R);
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     c[r * 32 + lane] = L[r];
                 c[R * 32 + lane] = dprev;
+                c[(R + 1) * 32 + lane] = botA;
                 ck++;
             }
 
             // publish block b+1 of the reference events (overwrites block b-1)
             {
                 const int slot = ((b + 1) & 1) * 32 + lane;
-                ring[slot] = ynext;
-                ring[slot + 64] = ynext;
+                const float2 v = make_float2(yn0, yn1);
+                ring[slot] = v;
+                ring[slot + 64] = v;
             }
             __syncwarp();
         }

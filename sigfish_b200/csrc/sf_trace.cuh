@@ -15,7 +15,8 @@
 // no history needed) or at a wavefront checkpoint written by the score kernel; cells on the
 // restart front carry an "exit code" instead of a column, and if the path of the target cell
 // leaves the window through the front the pass is repeated from an earlier restart point with
-// that front cell as the new target.
+// that front cell as the new target.  The pass runs the score kernel's macro-steps (two columns per
+// lane per step) so that its checkpoints can be resumed as they are.
 #pragma once
 #include <cuda_runtime.h>
 #include "sf_types.cuh"
@@ -130,99 +131,127 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
     int result = -1;
     int ck_limit = grp.n_ck;        // only checkpoints below this index may be used
 
+    // The pass uses the score kernel's macro-steps (two columns per lane per step: lane l is on columns
+    // 2(T-l), 2(T-l)+1 at macro-step T) so that its checkpoints can be resumed as they are.
     for (int attempt = 0; attempt < 64; attempt++) {
         // choose the restart: latest checkpoint k (< ck_limit) whose whole front lies at least
-        // min_window columns before the target and after the segment's sentinel; else the sentinel
+        // min_window columns before the target and after the segment's sentinel; else the sentinel.
+        // Checkpoint k holds the state after macro-step T_k = 32*(k+1)*ck_every - 1: lane l's rows at
+        // column 2(T_k - l) + 1.
         int k = -1;
         if (grp.ck_every > 0) {
-            // checkpoint k holds the state after step T_k = 32*(k+1)*ck_every - 1
-            const long long lim = (long long)tpos - a.min_window - 1;
-            long long kk = (lim + 1) / (32ll * grp.ck_every) - 1;
+            const long long lim = ((long long)tpos - a.min_window - 2) >> 1; // 2*T_k + 1 <= tpos - min_window - 1
+            long long kk = lim >= 0 ? (lim + 1) / (32ll * grp.ck_every) - 1 : -1;
             if (kk >= ck_limit) kk = ck_limit - 1;
             if (kk >= 0) {
                 const long long Tk = 32ll * (kk + 1) * grp.ck_every - 1;
-                if (Tk - 31 > seg_lo - 1) k = (int)kk;
+                if (2 * (Tk - 31) >= seg_lo) k = (int)kk; // every front cell lies inside the segment
             }
         }
         float L[R];
         int S[R];
-        float bot, dprev;
-        int sbot, sdprev;
-        int t0; // first step to execute
+        float botA, botB, dprev;
+        int sbotA, sbotB, sdprev;
+        int T0; // first macro-step to execute
         int T = 0;
         if (k >= 0) {
+            // Front cells carry an exit code instead of a start column: -1 - (4*row + off), the cell being
+            // (row, 2(T - row/R) + 1 - off): off 0 = the lane's second column (L), off 1 = its first column
+            // (bottom row only: botA), off 2 = the previous pair's second column (bottom row only: the next
+            // lane's dprev).
             T = 32 * (k + 1) * grp.ck_every - 1;
-            const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + k) * (size_t)((R + 1) * 32);
+            const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + k) * (size_t)sf_ckpt_floats(R);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 L[r] = c[r * 32 + lane];
-                S[r] = -1 - 2 * (lane * R + r);          // front cell (row, T - lane)
+                S[r] = -1 - 4 * (lane * R + r);
             }
             dprev = c[R * 32 + lane];
-            sdprev = -1 - (2 * (lane * R - 1) + 1);      // front cell (lane*R - 1, T - lane)
-            t0 = T + 1;
+            sdprev = -1 - (4 * (lane * R - 1) + 2);
+            botA = c[(R + 1) * 32 + lane];
+            sbotA = -1 - (4 * (lane * R + R - 1) + 1);
+            T0 = T + 1;
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) { L[r] = SF_INF; S[r] = 0; }
             dprev = (lane == 0 && !STD) ? 0.0f : SF_INF;
             sdprev = 0;
-            t0 = seg_lo - 1; // lane 0 starts on the sentinel
+            botA = SF_INF;
+            sbotA = 0;
+            T0 = (seg_lo - 1) >> 1; // lane 0 starts on the pair that holds the sentinel
         }
-        bot = L[R - 1];
-        sbot = S[R - 1];
+        botB = L[R - 1];
+        sbotB = S[R - 1];
         const int tl = trow / R, tr = trow % R;
-        const int t_end = tpos + tl; // step at which the target cell is produced
+        const int T_end = (tpos >> 1) + tl; // macro-step at which the target cell is produced
+        const int tb = tpos & 1;            // target in the first (0) or second (1) column of the pair
         int sres = 0;
-        // reference events are fetched 32 steps at a time (one coalesced load per lane) and handed to the
-        // lanes by shuffle: lane l needs position t - l, which sits in this block's or the previous block's load
-        float yprev;
+        // reference events: 32 pairs at a time, handed to the lanes by shuffle
+        float yp0, yp1;
         {
-            const int pp = t0 - 32 + lane;
-            yprev = (pp >= 0 && pp < n_pos) ? __ldg(y + pp) : SF_INF;
+            const long long c0 = 2ll * (T0 - 32 + lane);
+            yp0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
+            yp1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
         }
-        const int n_blk = (t_end - t0) / 32 + 1;
+        const int n_blk = (T_end - T0) / 32 + 1;
         for (int blk = 0; blk < n_blk; blk++) {
-            const int tb = t0 + 32 * blk;
-            const int pc = tb + lane;
-            const float ycur = (pc >= 0 && pc < n_pos) ? __ldg(y + pc) : SF_INF;
-#pragma unroll 4
+            const int Tb = T0 + 32 * blk;
+            const long long c0 = 2ll * (Tb + lane);
+            const float yc0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
+            const float yc1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
+#pragma unroll 2
             for (int s32 = 0; s32 < 32; s32++) {
-                const int t = tb + s32;
-                const int pos = t - lane;
+                const int Tm = Tb + s32;
+                const int colA = 2 * (Tm - lane);
                 const int src = (s32 - lane) & 31;
-                const float ya = __shfl_sync(full, ycur, src);
-                const float yb = __shfl_sync(full, yprev, src);
-                const float yy = s32 >= lane ? ya : yb;
-                float up = __shfl_up_sync(full, bot, 1);
-                int sup = __shfl_up_sync(full, sbot, 1);
+                const float a0 = __shfl_sync(full, yc0, src), a1 = __shfl_sync(full, yc1, src);
+                const float b0 = __shfl_sync(full, yp0, src), b1 = __shfl_sync(full, yp1, src);
+                const float yA = s32 >= lane ? a0 : b0;
+                const float yB = s32 >= lane ? a1 : b1;
+                float upA = __shfl_up_sync(full, botA, 1);
+                float upB = __shfl_up_sync(full, botB, 1);
+                int supA = __shfl_up_sync(full, sbotA, 1);
+                int supB = __shfl_up_sync(full, sbotB, 1);
                 if (lane == 0) {
-                    up = STD ? (yy == SF_INF ? 0.0f : SF_INF) : 0.0f;
-                    sup = 0;
+                    upA = STD ? (yA == SF_INF ? 0.0f : SF_INF) : 0.0f;
+                    upB = STD ? (yB == SF_INF ? 0.0f : SF_INF) : 0.0f;
+                    supA = 0;
+                    supB = 0;
                 }
-                const float unext = up;
-                const int sunext = sup;
-                float dg = dprev;
-                int sdg = sdprev;
+                const float next_dprev = upB;
+                const int next_sdprev = supB;
+                float dgA = dprev, dgB = upA;
+                int sdgA = sdprev, sdgB = supA;
+                int capA = 0, capB = 0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const float m = fminf(fminf(up, dg), L[r]);
-                    int s = (dg == m) ? sdg : ((L[r] == m) ? S[r] : sup);
+                    // first column: left = L[r] (previous macro-step's second column)
+                    const float mA = fminf(fminf(upA, dgA), L[r]);
+                    int sA = (dgA == mA) ? sdgA : ((L[r] == mA) ? S[r] : supA);
                     if (lane == 0 && r == 0)
-                        s = pos - seg_lo; // start(0, j) = j
-                    const float nv = fabsf(x[r] - yy) + m;
-                    dg = L[r]; sdg = S[r];
-                    L[r] = nv; S[r] = s;
-                    up = nv; sup = s;
+                        sA = colA - seg_lo; // start(0, j) = j
+                    const float va = fabsf(x[r] - yA) + mA;
+                    // second column: left = the value just computed
+                    const float mB = fminf(fminf(upB, dgB), va);
+                    int sB = (dgB == mB) ? sdgB : ((va == mB) ? sA : supB);
+                    if (lane == 0 && r == 0)
+                        sB = colA + 1 - seg_lo;
+                    const float vb = fabsf(x[r] - yB) + mB;
+                    dgA = L[r]; sdgA = S[r];
+                    dgB = va; sdgB = sA;
+                    L[r] = vb; S[r] = sB;
+                    upA = va; supA = sA;
+                    upB = vb; supB = sB;
+                    if (r == tr) { capA = sA; capB = sB; }
                 }
-                dprev = unext; sdprev = sunext;
-                bot = L[R - 1]; sbot = S[R - 1];
-                if (t == t_end) {
-#pragma unroll
-                    for (int r = 0; r < R; r++)
-                        if (r == tr) sres = S[r];
-                }
+                dprev = next_dprev; sdprev = next_sdprev;
+                botA = upA; sbotA = supA;
+                botB = upB; sbotB = supB;
+                if (Tm == T_end)
+                    sres = tb ? capB : capA;
             }
-            yprev = ycur;
+            yp0 = yc0;
+            yp1 = yc1;
         }
         sres = __shfl_sync(full, sres, tl);
         if (sres >= 0 || k < 0) {
@@ -231,8 +260,8 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
         }
         // the path left the window through the restart front: continue from that cell
         const int code = -1 - sres;
-        trow = code >> 1;
-        tpos = T - trow / R - (code & 1);
+        trow = code >> 2;
+        tpos = 2 * (T - trow / R) + 1 - (code & 3);
         ck_limit = k; // strictly earlier restart next time
     }
     hit.pos_st = result;

@@ -179,7 +179,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         SF_CUDA(c, cudaMalloc(&s.d_info, sizeof(sf_readinfo) * n));
         SF_CUDA(c, cudaMalloc(&s.d_res, sizeof(sf_taskres) * n * std::max(1, c->n_groups)));
         if (c->ck_per_read > 0)
-            SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)((c->R + 1) * 32)));
+            SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)sf_ckpt_floats(c->R)));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
         SF_CUDA(c, cudaMalloc(&s.d_polya, sizeof(int64_t) * n));
         if (c->opt.flags & SFGPU_SAM) {
@@ -466,8 +466,8 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
         if (longest > c->ck_min_cols) {
             // checkpoint period: ~1/256 of the segment, between ck_min_cols/4 (512) and 4096 columns
             const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, std::min<int64_t>(4096, longest / 256));
-            g.ck_every = (int32_t)((cols_per + 31) / 32);
-            g.n_ck = (int32_t)(((g.end - g.begin) / 32) / g.ck_every);
+            g.ck_every = (int32_t)((cols_per + SF_BLOCK_COLS - 1) / SF_BLOCK_COLS); // in blocks of 64 columns
+            g.n_ck = (int32_t)(((g.end - g.begin) / SF_BLOCK_COLS) / g.ck_every);
         }
         for (int s = s0; s < s1; s++)
             c->seg_group[s] = (int32_t)c->groups.size();
@@ -1136,5 +1136,13 @@ int sfgpu_query(sfgpu_ctx *c, int32_t slot, int32_t read, float *out, int32_t ca
 }
 
 int64_t sfgpu_ref_columns(const sfgpu_ctx *c) { return c ? c->ref_columns : 0; }
+
+int32_t sfgpu_wave_reads(const sfgpu_ctx *c)
+{
+    if (!c || !c->have_ref || c->n_groups <= 0)
+        return 0;
+    const int64_t warps = (int64_t)c->sm_count * c->dtw_blocks_per_sm * SF_DTW_WARPS;
+    return (int32_t)std::max<int64_t>(1, warps / c->n_groups);
+}
 
 } // extern "C"
