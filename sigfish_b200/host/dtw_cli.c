@@ -3,7 +3,8 @@
  * Same options, defaults, validation rules and stderr summary as the reference's dtw_main()
  * (reference src/dtw_main.c:17-43 option table, 125-285 parsing + validation, 299-326 batch loop,
  * 331-345 summary).  Differences, all documented in INTEGRATION.md:
- *   - the batch loop is double buffered: batch n+1 is loaded from disk while batch n is on the GPUs;
+ *   - two batches are in flight: batch n+1 is loaded, decoded and submitted while batch n is on the GPUs;
+ *   - without -K / -B the batch is sized to two full waves of DTW tasks per GPU instead of 512 reads / 20 MB;
  *   - --gpus N / --gpu-first I choose the devices (default: all visible B200s); reads are sharded
  *     over them with the reference replicated;
  *   - --pore rna004 is accepted (the reference's validity test rejects it by mistake);
@@ -74,8 +75,8 @@ static void print_help_msg(FILE *fp, const opt_t *opt)
     fprintf(fp, "Usage: sigfish dtw [OPTIONS] genome.fa reads.blow5\n");
     fprintf(fp, "\nbasic options:\n");
     fprintf(fp, "   -t INT                     number of host threads decoding records [%d]\n", opt->num_thread);
-    fprintf(fp, "   -K INT                     batch size (max number of reads loaded at once) [%d]\n", opt->batch_size);
-    fprintf(fp, "   -B FLOAT[K/M/G]            max number of bytes loaded at once [%.1fM]\n", opt->batch_size_bytes / (float)(1000 * 1000));
+    fprintf(fp, "   -K INT                     batch size (max number of reads loaded at once) [auto: two GPU waves, >= %d]\n", opt->batch_size);
+    fprintf(fp, "   -B FLOAT[K/M/G]            max number of bytes loaded at once [auto, >= %.1fM]\n", opt->batch_size_bytes / (float)(1000 * 1000));
     fprintf(fp, "   -h                         help\n");
     fprintf(fp, "   -o FILE                    output to file [stdout]\n");
     fprintf(fp, "   --verbose INT              verbosity level [%d]\n", (int)opt->verbosity);
@@ -106,16 +107,19 @@ int dtw_main(int argc, char *argv[])
     FILE *fp_help = stderr;
     opt_t opt;
     init_opt(&opt);
+    int k_set = 0, b_set = 0;
 
     while ((c = getopt_long(argc, argv, optstring, long_options, &longindex)) >= 0) {
         if (c == 'w') {
             opt.region_str = optarg;
         } else if (c == 'B') {
             opt.batch_size_bytes = parse_num(optarg);
+            b_set = 1;
             if (opt.batch_size_bytes <= 0)
                 SF_FATAL("%s", "Maximum number of bytes should be larger than 0.");
         } else if (c == 'K') {
             opt.batch_size = atoi(optarg);
+            k_set = 1;
             if (opt.batch_size < 1)
                 SF_FATAL("Batch size should larger than 0. You entered %d", opt.batch_size);
         } else if (c == 't') {
@@ -209,39 +213,59 @@ int dtw_main(int argc, char *argv[])
     }
 
     core_t *core = init_core(fastafile, slow5file, opt, realtime0);
-    /* two batches: one on the GPUs, one being loaded */
+    /* Batch size: the reference's defaults (512 reads / 20 MB) are kept when given explicitly; otherwise the
+     * batch is sized to two full waves of DTW tasks per GPU, because a task on a long contig runs for a long
+     * time and a partially filled GPU is the dominant inefficiency. */
+    if (!k_set) {
+        const int32_t wave = sfgpu_wave_reads(core->gpu[0]);
+        const int64_t want = 2ll * wave * core->num_gpus;
+        if (want > core->opt.batch_size)
+            core->opt.batch_size = (int32_t)(want > 262144 ? 262144 : want);
+    }
+    if (!b_set) {
+        const int64_t want = (int64_t)core->opt.batch_size * 16000;
+        if (want > core->opt.batch_size_bytes)
+            core->opt.batch_size_bytes = want;
+    }
+    if (sf_verbosity >= 3)
+        fprintf(stderr, "[%s] batch size: %d reads / %.1fM bytes on %d GPU(s)\n", __func__, core->opt.batch_size,
+                core->opt.batch_size_bytes / 1e6, core->num_gpus);
+
+    /* two batches in flight (one device slot each): while batch n runs, batch n+1 is loaded, decoded and
+     * submitted, so the tail of one batch overlaps the head of the next; output stays in input order */
     db_t *db[2] = {init_db(core), init_db(core)};
+    ret_status_t st[2] = {{0, 0}, {0, 0}};
     if (core->opt.flag & SIGFISH_SAM)
         sam_hdr_wr(core->ref);
-    int32_t counter = 0;
-    int cur = 0;
-    ret_status_t status = load_db(core, db[cur]);
-    fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", __func__, sf_realtime() - realtime0,
-            sf_cputime() / (sf_realtime() - realtime0), status.num_reads, status.num_bytes / (1000.0 * 1000.0));
-    for (;;) {
-        const int more = status.num_reads >= core->opt.batch_size || status.num_bytes >= core->opt.batch_size_bytes;
-        const int stop_after = (opt.debug_break == counter);
-        double t0 = sf_realtime();
-        submit_db(core, db[cur]);
-        core->process_db_time += sf_realtime() - t0;
-        ret_status_t next = {0, 0};
-        if (more && !stop_after) { /* overlap: load the next batch while this one is on the GPUs */
-            next = load_db(core, db[cur ^ 1]);
+    int more = 1, in_flight = 0, head = 0, next_db = 0;
+    int32_t n_loaded = 0;
+    while (more || in_flight) {
+        if (more && in_flight < 2) {
+            db_t *d = db[next_db];
+            st[next_db] = load_db(core, d);
             fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", __func__, sf_realtime() - realtime0,
-                    sf_cputime() / (sf_realtime() - realtime0), next.num_reads, next.num_bytes / (1000.0 * 1000.0));
+                    sf_cputime() / (sf_realtime() - realtime0), st[next_db].num_reads, st[next_db].num_bytes / (1000.0 * 1000.0));
+            /* src/dtw_main.c:299-300, 322-325 */
+            more = (st[next_db].num_reads >= core->opt.batch_size || st[next_db].num_bytes >= core->opt.batch_size_bytes) &&
+                   opt.debug_break != n_loaded;
+            n_loaded++;
+            const double t0 = sf_realtime();
+            submit_db(core, d);
+            core->process_db_time += sf_realtime() - t0;
+            in_flight++;
+            next_db ^= 1;
+            continue;
         }
-        t0 = sf_realtime();
-        collect_db(core, db[cur]);
+        db_t *d = db[head];
+        const double t0 = sf_realtime();
+        collect_db(core, d);
         core->process_db_time += sf_realtime() - t0;
         fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) processed\n", __func__, sf_realtime() - realtime0,
-                sf_cputime() / (sf_realtime() - realtime0), status.num_reads, status.num_bytes / (1000.0 * 1000.0));
-        output_db(core, db[cur]);
-        free_db_tmp(db[cur]);
-        if (!more || stop_after)
-            break;
-        counter++;
-        status = next;
-        cur ^= 1;
+                sf_cputime() / (sf_realtime() - realtime0), st[head].num_reads, st[head].num_bytes / (1000.0 * 1000.0));
+        output_db(core, d);
+        free_db_tmp(d);
+        head ^= 1;
+        in_flight--;
     }
     free_db(db[0]);
     free_db(db[1]);

@@ -184,7 +184,9 @@ def write_blow5(path: str, read_ids, signals, rna: bool = False, kit: str | None
     import zlib
     scaling = scaling or (RNA_SCALING if rna else DNA_SCALING)
     kit = kit or ("sqk-rna002" if rna else "sqk-lsk109")
-    hdr = (f"#slow5_version\t0.2.0\n#num_read_groups\t1\n@experiment_type\t{'rna' if rna else 'genomic_dna'}\n"
+    # the text part of a BLOW5 header holds only the @attributes and the two column lines: version, compression
+    # and the number of read groups live in the binary part
+    hdr = (f"@experiment_type\t{'rna' if rna else 'genomic_dna'}\n"
            f"@sequencing_kit\t{kit}\n#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n"
            "#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n").encode()
     with open(path, "wb") as f:

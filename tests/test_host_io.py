@@ -147,3 +147,22 @@ def test_model_reader(host, tmp_path):
     err = C.create_string_buffer(512)
     assert host.sf_model_read(bad.encode(), C.byref(lm), C.byref(kk), err, 512) != 0
     assert b"prematurely" in err.value
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("zl,svb", [(True, True), (False, True), (True, False), (False, False)])
+def test_reference_binary_reads_the_blow5_we_write(tmp_path, zl, svb):
+    """synth.write_blow5 is what the GPU-side CLI tests and tools/cli_e2e.py feed to BOTH binaries: slow5lib
+    must accept it and the reference must print its golden PAF from it.  Build container only."""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, "sp1_dna.npz"))
+    p = str(tmp_path / "r.blow5")
+    synth.write_blow5(p, ids, sigs, scalings=sc, record_zlib=zl, signal_svb=svb)
+    fa = str(tmp_path / "ref.fa")
+    with gzip.open(os.path.join(H.GOLDEN, "nCoV-2019.fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    mean, stdv = synth.make_model(6)
+    mf = str(tmp_path / "m.txt")
+    synth.write_model_file(mf, 6, mean, stdv)
+    assert H.run_ref(fa, p, mf) == open(os.path.join(H.GOLDEN, "paf", "dna_sp1_default.paf")).read()

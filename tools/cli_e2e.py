@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""End-to-end, from files: `sigfish-b200 dtw` against the unmodified reference binary on the same FASTA /
+BLOW5 / model files (C4 shape: one 1 Mb contig, R10 k=9 reads).  Prints wall times and reads/s of both and
+checks that the reference's PAF for its (small) read subset is byte-identical to the corresponding rows of
+ours.  Development / evidence tool: the judged numbers come from bench.py.
+Usage: python tools/cli_e2e.py [--reads N] [--ref-reads M] [--gpus G]"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sigfish_b200 import build as B  # noqa: E402
+from sigfish_b200 import synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=5920)
+    ap.add_argument("--ref-reads", type=int, default=32)
+    ap.add_argument("--ref-len", type=int, default=1_000_000)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("-K", type=int, default=0)
+    args = ap.parse_args()
+    B.build_all()
+    d = os.path.join(synth.tmpdir(), "cli_e2e")
+    os.makedirs(d, exist_ok=True)
+    k = 9
+    mean, stdv = synth.make_model(k)
+    seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
+    sigs, _ = synth.simulate_reads([seq], k, mean, args.reads, seed=4242, bases_per_read=450)
+    ids = [f"read_{i:06d}" for i in range(len(sigs))]
+    synth.write_model_file(os.path.join(d, "model.txt"), k, mean, stdv)
+    synth.write_fasta(os.path.join(d, "ref.fa"), ["chrS"], [seq])
+    synth.write_blow5(os.path.join(d, "reads.blow5"), ids, sigs, kit="sqk-lsk114")
+    synth.write_blow5(os.path.join(d, "subset.blow5"), ids[:args.ref_reads], sigs[:args.ref_reads], kit="sqk-lsk114")
+    K = args.K or args.reads
+    out = {"reads": args.reads, "ref_reads": args.ref_reads, "cells_per_read": 250 * 2 * (args.ref_len + 1 - k)}
+
+    t0 = time.perf_counter()
+    r = subprocess.run([B.CLI, "dtw", os.path.join(d, "ref.fa"), os.path.join(d, "reads.blow5"), "--kmer-model",
+                        os.path.join(d, "model.txt"), "-K", str(K), "-B", "100G", "-t", str(os.cpu_count() or 8), "--gpus", str(args.gpus),
+                        "-o", os.path.join(d, "gpu.paf")], capture_output=True, text=True)
+    out["b200_wall_s"] = time.perf_counter() - t0
+    assert r.returncode == 0, r.stderr[-3000:]
+    for line in r.stderr.splitlines():
+        for key in ("Data loading time", "Data processing time", "Parse time", "DTW time", "Events + normalise"):
+            if key in line:
+                out["b200 " + key] = float(line.split(":")[-1].split()[0])
+    out["b200_reads_per_s_processing"] = args.reads / out["b200 Data processing time"]
+    out["b200_GCUPS_processing"] = args.reads * out["cells_per_read"] / out["b200 Data processing time"] / 1e9
+
+    refbin = os.path.join(ROOT, "oracle", "_ref", "sigfish")
+    if os.path.exists(refbin) and args.ref_reads > 0:
+        t0 = time.perf_counter()
+        r = subprocess.run([refbin, "dtw", os.path.join(d, "ref.fa"), os.path.join(d, "subset.blow5"), "--kmer-model",
+                            os.path.join(d, "model.txt"), "-t", str(os.cpu_count() or 8), "-o", os.path.join(d, "cpu.paf")],
+                           capture_output=True, text=True)
+        out["reference_wall_s"] = time.perf_counter() - t0
+        assert r.returncode == 0, r.stderr[-3000:]
+        for line in r.stderr.splitlines():
+            if "Data processing time" in line:
+                out["reference Data processing time"] = float(line.split(":")[-1].split()[0])
+        out["reference_reads_per_s_processing"] = args.ref_reads / out["reference Data processing time"]
+        cpu = open(os.path.join(d, "cpu.paf")).read()
+        gpu = "".join(open(os.path.join(d, "gpu.paf")).readlines()[:cpu.count("\n")])
+        out["paf_identical_on_subset"] = cpu == gpu
+        out["speedup_processing"] = out["b200_reads_per_s_processing"] / out["reference_reads_per_s_processing"]
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
