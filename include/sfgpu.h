@@ -105,6 +105,13 @@ int sfgpu_submit(sfgpu_ctx *ctx, int32_t slot, int32_t n_reads, const int16_t *s
                  const int64_t *sig_off, const float *digitisation, const float *offset,
                  const float *range);
 
+/* sfgpu_submit with one pointer per read (signals[i] holds n_samples[i] samples), so that a host that keeps
+ * its reads in separate buffers, like db->slow5_rec[i]->raw_signal (src/sigfish.h:168), needs no gather
+ * copy: the samples go straight into the slot's pinned staging buffer. */
+int sfgpu_submit_reads(sfgpu_ctx *ctx, int32_t slot, int32_t n_reads, const int16_t *const *signals,
+                       const int64_t *n_samples, const float *digitisation, const float *offset,
+                       const float *range);
+
 /* Same as sfgpu_submit but re-runs the device stages on the inputs already resident in the slot
  * (no host->device copy).  Used to measure device-only throughput. */
 int sfgpu_resubmit(sfgpu_ctx *ctx, int32_t slot);

@@ -17,7 +17,8 @@ SFGPU_RNA, SFGPU_DTW, SFGPU_INV, SFGPU_REF, SFGPU_END, SFGPU_SAM = 0x001, 0x002,
 SYMBOLS = ["sfgpu_device_count", "sfgpu_create", "sfgpu_set_ref", "sfgpu_submit", "sfgpu_resubmit",
            "sfgpu_collect", "sfgpu_timing", "sfgpu_destroy", "sfgpu_strerror", "sfgpu_ref_events",
            "sfgpu_event_table", "sfgpu_query", "sfgpu_ref_columns", "sfgpu_set_ref_events",
-           "sfgpu_submit_queries", "sfgpu_collect_paths", "sfgpu_wave_reads"]
+           "sfgpu_submit_queries", "sfgpu_collect_paths", "sfgpu_wave_reads",
+           "sfgpu_submit_reads"]
 
 
 class Opt(C.Structure):
@@ -62,6 +63,7 @@ def lib():
     L.sfgpu_create.argtypes = [C.POINTER(vp), C.POINTER(Opt), vp]
     L.sfgpu_set_ref.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_submit.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    L.sfgpu_submit_reads.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_resubmit.argtypes = [vp, C.c_int32]
     L.sfgpu_collect.argtypes = [vp, C.c_int32, vp]
     L.sfgpu_timing.argtypes = [vp, C.c_int32, C.POINTER(Timing)]
@@ -179,6 +181,19 @@ class Context:
         n = off.shape[0] - 1
         self._check(lib().sfgpu_submit(self._h, slot, n, _ptr(flat), _ptr(off), _ptr(dig), _ptr(offs), _ptr(rng)),
                     "sfgpu_submit")
+        self._n[slot] = n
+
+    def submit_reads(self, slot, signals, scalings):
+        """one buffer per read (sfgpu_submit_reads): no gather copy on the caller's side"""
+        n = len(signals)
+        keep = [np.ascontiguousarray(s, dtype=np.int16) for s in signals]
+        ptrs = (C.c_void_p * max(n, 1))(*[k.ctypes.data for k in keep])
+        lens = np.array([len(k) for k in keep] or [0], dtype=np.int64)
+        dig = np.array([sc["digitisation"] for sc in scalings] or [0], dtype=np.float32)
+        offs = np.array([sc["offset"] for sc in scalings] or [0], dtype=np.float32)
+        rng = np.array([sc["range"] for sc in scalings] or [0], dtype=np.float32)
+        self._check(lib().sfgpu_submit_reads(self._h, slot, n, ptrs, _ptr(lens), _ptr(dig), _ptr(offs), _ptr(rng)),
+                    "sfgpu_submit_reads")
         self._n[slot] = n
 
     def resubmit(self, slot):

@@ -502,6 +502,59 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
     return SFGPU_OK;
 }
 
+// common part of sfgpu_submit / sfgpu_submit_reads: read i is `len(i)` samples at `ptr(i)`
+template <typename PtrFn, typename LenFn>
+int submit_common(sfgpu_ctx *c, int32_t slot, int32_t n_reads, PtrFn ptr, LenFn len_of,
+                         const float *digitisation, const float *offset, const float *range)
+{
+    if (!c->have_ref)
+        return fail(c, SFGPU_ESTATE, "sfgpu_submit before sfgpu_set_ref");
+    if (slot < 0 || slot >= (int)c->slots.size() || n_reads < 0)
+        return fail(c, SFGPU_EARG, "bad slot or read count");
+    if (n_reads > 0 && (!digitisation || !offset || !range))
+        return fail(c, SFGPU_EARG, "null batch array");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    // every read starts on a 16-byte boundary so that the event kernel can use 16-byte loads
+    int64_t padded = 0, raw = 0;
+    for (int i = 0; i < n_reads; i++) {
+        const int64_t len = len_of(i);
+        if (len < 0 || (len > 0 && !ptr(i)))
+            return fail(c, SFGPU_EARG, "bad signal pointer / length for read %d", i);
+        padded += (len + 7) & ~7ll;
+        raw += len;
+    }
+    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8);
+    if (rc)
+        return rc;
+    int64_t cur = 0;
+    int64_t *h_len = s.h_off + (n_reads + 1);
+    for (int i = 0; i < n_reads; i++) {
+        const int64_t len = len_of(i);
+        s.h_off[i] = cur;
+        h_len[i] = len;
+        if (len > 0)
+            memcpy(s.h_signal + cur, ptr(i), sizeof(int16_t) * (size_t)len);
+        const int64_t end = cur + ((len + 7) & ~7ll);
+        for (int64_t j = cur + len; j < end; j++)
+            s.h_signal[j] = 0;
+        cur = end;
+        s.h_scal[i] = digitisation[i];
+        s.h_scal[s.cap_reads + i] = offset[i];
+        s.h_scal[2 * (size_t)s.cap_reads + i] = range[i];
+    }
+    s.h_off[n_reads] = cur;
+    s.n_reads = n_reads;
+    s.n_samples = cur;
+    s.raw_samples = raw;
+    s.queries_only = false;
+    return run_stages(c, s, true);
+}
+
+
 } // namespace
 
 extern "C" {
@@ -766,50 +819,22 @@ int sfgpu_submit(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_t *sig
 {
     if (!c)
         return fail(nullptr, SFGPU_EARG, "null context");
-    if (!c->have_ref)
-        return fail(c, SFGPU_ESTATE, "sfgpu_submit before sfgpu_set_ref");
-    if (slot < 0 || slot >= (int)c->slots.size() || n_reads < 0)
-        return fail(c, SFGPU_EARG, "bad slot or read count");
-    if (n_reads > 0 && (!signals || !sig_off || !digitisation || !offset || !range))
+    if (n_reads > 0 && (!signals || !sig_off))
         return fail(c, SFGPU_EARG, "null batch array");
-    SF_CUDA(c, cudaSetDevice(c->opt.device));
-    sf_slot &s = c->slots[slot];
-    int rc = slot_wait(c, s);
-    if (rc)
-        return rc;
-    // every read starts on a 16-byte boundary so that the event kernel can use 16-byte loads
-    int64_t padded = 0, raw = 0;
-    for (int i = 0; i < n_reads; i++) {
-        const int64_t len = sig_off[i + 1] - sig_off[i];
-        if (len < 0)
-            return fail(c, SFGPU_EARG, "negative signal length for read %d", i);
-        padded += (len + 7) & ~7ll;
-        raw += len;
-    }
-    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8);
-    if (rc)
-        return rc;
-    int64_t cur = 0;
-    int64_t *h_len = s.h_off + (n_reads + 1);
-    for (int i = 0; i < n_reads; i++) {
-        const int64_t len = sig_off[i + 1] - sig_off[i];
-        s.h_off[i] = cur;
-        h_len[i] = len;
-        memcpy(s.h_signal + cur, signals + sig_off[i], sizeof(int16_t) * (size_t)len);
-        const int64_t end = cur + ((len + 7) & ~7ll);
-        for (int64_t j = cur + len; j < end; j++)
-            s.h_signal[j] = 0;
-        cur = end;
-        s.h_scal[i] = digitisation[i];
-        s.h_scal[s.cap_reads + i] = offset[i];
-        s.h_scal[2 * (size_t)s.cap_reads + i] = range[i];
-    }
-    s.h_off[n_reads] = cur;
-    s.n_reads = n_reads;
-    s.n_samples = cur;
-    s.raw_samples = raw;
-    s.queries_only = false;
-    return run_stages(c, s, true);
+    return submit_common(c, slot, n_reads, [&](int i) { return signals + sig_off[i]; },
+                         [&](int i) { return sig_off[i + 1] - sig_off[i]; }, digitisation, offset, range);
+}
+
+int sfgpu_submit_reads(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_t *const *signals,
+                       const int64_t *n_samples, const float *digitisation, const float *offset,
+                       const float *range)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (n_reads > 0 && (!signals || !n_samples))
+        return fail(c, SFGPU_EARG, "null batch array");
+    return submit_common(c, slot, n_reads, [&](int i) { return signals[i]; }, [&](int i) { return n_samples[i]; },
+                         digitisation, offset, range);
 }
 
 int sfgpu_submit_queries(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const float *queries,

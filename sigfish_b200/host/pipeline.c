@@ -102,6 +102,44 @@ static int8_t pore_detect(const sf_s5file_t *sf)
     return pore;
 }
 
+typedef struct {
+    core_t *core;
+    int g, device;
+    const opt_t *opt;
+    const sf_fasta_t *fa;
+    int write_ref; /* only one worker fills the shared ref_lengths / offsets arrays */
+    int failed;
+    char err[512];
+} gpu_init_arg_t;
+
+static void *gpu_init_worker(void *p)
+{
+    gpu_init_arg_t *a = (gpu_init_arg_t *)p;
+    core_t *core = a->core;
+    const opt_t *opt = a->opt;
+    sfgpu_opt_t go;
+    memset(&go, 0, sizeof go);
+    go.device = a->device;
+    go.flags = opt->flag & (SFGPU_RNA | SFGPU_DTW | SFGPU_INV | SFGPU_REF | SFGPU_END | SFGPU_SAM);
+    go.query_size = opt->query_size;
+    go.prefix_size = opt->prefix_size;
+    go.kmer_size = (int32_t)core->kmer_size;
+    go.n_slots = 2;
+    go.pore = opt->pore_flag;
+    if (sfgpu_create(&core->gpu[a->g], &go, core->level_mean) != SFGPU_OK) {
+        snprintf(a->err, sizeof a->err, "%s", sfgpu_strerror(NULL));
+        a->failed = 1;
+        return NULL;
+    }
+    refsynth_t *ref = core->ref;
+    if (sfgpu_set_ref(core->gpu[a->g], a->fa->num_ref, a->fa->bases, a->fa->off, a->write_ref ? ref->ref_lengths : NULL,
+                      a->write_ref ? ref->ref_seq_lengths : NULL, a->write_ref ? ref->ref_st_offset : NULL) != SFGPU_OK) {
+        snprintf(a->err, sizeof a->err, "%s", sfgpu_strerror(core->gpu[a->g]));
+        a->failed = 1;
+    }
+    return NULL;
+}
+
 core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double realtime0)
 {
     core_t *core = (core_t *)calloc(1, sizeof(core_t));
@@ -173,23 +211,33 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
     if (bad)
         SF_WARNING("%ld non-ACGT reference bases are treated as 'A' (reverse strand: 'T'), as in the reference", (long)bad);
 
-    for (int g = 0; g < core->num_gpus; g++) {
-        sfgpu_opt_t go;
-        memset(&go, 0, sizeof go);
-        go.device = first + g;
-        go.flags = opt.flag & (SFGPU_RNA | SFGPU_DTW | SFGPU_INV | SFGPU_REF | SFGPU_END | SFGPU_SAM);
-        go.query_size = opt.query_size;
-        go.prefix_size = opt.prefix_size;
-        go.kmer_size = (int32_t)core->kmer_size;
-        go.n_slots = 2;
-        go.pore = opt.pore_flag;
-        if (sfgpu_create(&core->gpu[g], &go, core->level_mean) != SFGPU_OK) {
-            SF_FATAL("GPU %d: %s", first + g, sfgpu_strerror(NULL));
+    /* one context per GPU, each with the whole reference; built concurrently (CUDA context creation and the
+     * serial-order z-score of a long contig take ~1 s per device) */
+    {
+        gpu_init_arg_t *ia = (gpu_init_arg_t *)calloc((size_t)core->num_gpus, sizeof(gpu_init_arg_t));
+        pthread_t *tid = (pthread_t *)calloc((size_t)core->num_gpus, sizeof(pthread_t));
+        for (int g = 0; g < core->num_gpus; g++) {
+            ia[g].core = core;
+            ia[g].g = g;
+            ia[g].device = first + g;
+            ia[g].opt = &opt;
+            ia[g].fa = &fa;
+            ia[g].write_ref = g == 0;
+            if (core->num_gpus == 1)
+                gpu_init_worker(&ia[g]);
+            else if (pthread_create(&tid[g], NULL, gpu_init_worker, &ia[g])) {
+                SF_FATAL("%s", "pthread_create failed");
+            }
         }
-        if (sfgpu_set_ref(core->gpu[g], fa.num_ref, fa.bases, fa.off, ref->ref_lengths, ref->ref_seq_lengths,
-                          ref->ref_st_offset) != SFGPU_OK) {
-            SF_FATAL("GPU %d: %s", first + g, sfgpu_strerror(core->gpu[g]));
+        for (int g = 0; g < core->num_gpus; g++) {
+            if (core->num_gpus > 1)
+                pthread_join(tid[g], NULL);
+            if (ia[g].failed) {
+                SF_FATAL("GPU %d: %s", first + g, ia[g].err);
+            }
         }
+        free(ia);
+        free(tid);
     }
     free(fa.bases);
     free(fa.off);
@@ -231,6 +279,7 @@ db_t *init_db(core_t *core)
     db->aln = (aln_t *)calloc(n, sizeof(aln_t));
     db->out = (char **)calloc(n, sizeof(char *));
     db->sig_off = (int64_t *)calloc(n + 1, sizeof(int64_t));
+    db->sig_ptr = (int16_t **)calloc(n, sizeof(int16_t *));
     db->dig = (float *)calloc(n, sizeof(float));
     db->off = (float *)calloc(n, sizeof(float));
     db->rng = (float *)calloc(n, sizeof(float));
@@ -356,6 +405,24 @@ void sf_shard_ranges(int32_t n_rec, const int64_t *n_samples, int32_t G, int32_t
     }
 }
 
+typedef struct {
+    core_t *core;
+    db_t *db;
+    int g;
+    int failed;
+} gpu_submit_arg_t;
+
+static void *gpu_submit_worker(void *p)
+{
+    gpu_submit_arg_t *a = (gpu_submit_arg_t *)p;
+    db_t *db = a->db;
+    const int b = db->shard_begin[a->g], e = db->shard_begin[a->g + 1];
+    if (sfgpu_submit_reads(a->core->gpu[a->g], db->slot, e - b, (const int16_t *const *)db->sig_ptr + b, db->sig_off + b,
+                           db->dig + b, db->off + b, db->rng + b) != SFGPU_OK)
+        a->failed = 1;
+    return NULL;
+}
+
 void submit_db(core_t *core, db_t *db)
 {
     const double t0 = sf_realtime();
@@ -375,29 +442,36 @@ void submit_db(core_t *core, db_t *db)
 
     db->slot = core->next_slot;
     core->next_slot ^= 1;
+    /* per-read pointers / lengths / scalings once for the whole batch; every shard is a sub-range */
+    for (int i = 0; i < db->n_rec; i++) {
+        const sf_rec_t *r = &db->rec[i];
+        db->sig_ptr[i] = r->raw_signal;
+        db->sig_off[i] = (int64_t)r->len_raw_signal; /* used as the length array here */
+        /* narrowed to float exactly as event_single() does (src/sigfish.c:335-337) */
+        db->dig[i] = (float)r->digitisation;
+        db->off[i] = (float)r->offset;
+        db->rng[i] = (float)r->range;
+    }
+    /* one host thread per GPU copies its shard into that GPU's pinned staging buffer and launches */
+    gpu_submit_arg_t sa[SFHOST_MAX_GPUS];
+    pthread_t tid[SFHOST_MAX_GPUS];
     for (g = 0; g < G; g++) {
-        const int b = db->shard_begin[g], e = db->shard_begin[g + 1];
-        /* gather the shard's signals into one host buffer; the library copies it into pinned staging */
-        int64_t n = 0;
-        for (int i = b; i < e; i++)
-            n += (int64_t)db->rec[i].len_raw_signal;
-        int16_t *flat = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n > 0 ? n : 1));
-        int64_t cur = 0;
-        for (int i = b; i < e; i++) {
-            const sf_rec_t *r = &db->rec[i];
-            db->sig_off[i - b] = cur;
-            memcpy(flat + cur, r->raw_signal, sizeof(int16_t) * (size_t)r->len_raw_signal);
-            cur += (int64_t)r->len_raw_signal;
-            /* narrowed to float exactly as event_single() does (src/sigfish.c:335-337) */
-            db->dig[i - b] = (float)r->digitisation;
-            db->off[i - b] = (float)r->offset;
-            db->rng[i - b] = (float)r->range;
+        sa[g].core = core;
+        sa[g].db = db;
+        sa[g].g = g;
+        sa[g].failed = 0;
+        if (G == 1)
+            gpu_submit_worker(&sa[g]);
+        else if (pthread_create(&tid[g], NULL, gpu_submit_worker, &sa[g])) {
+            SF_FATAL("%s", "pthread_create failed");
         }
-        db->sig_off[e - b] = cur;
-        if (sfgpu_submit(core->gpu[g], db->slot, e - b, flat, db->sig_off, db->dig, db->off, db->rng) != SFGPU_OK) {
+    }
+    for (g = 0; g < G; g++) {
+        if (G > 1)
+            pthread_join(tid[g], NULL);
+        if (sa[g].failed) {
             SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
         }
-        free(flat);
     }
     db->submitted = 1;
 }
@@ -675,7 +749,7 @@ void free_db(db_t *db)
         free(db->rec[i].raw_signal);
     }
     free(db->mem_records); free(db->mem_bytes); free(db->mem_cap); free(db->rec); free(db->res); free(db->aln);
-    free(db->out); free(db->sig_off); free(db->dig); free(db->off); free(db->rng);
+    free(db->out); free(db->sig_off); free(db->sig_ptr); free(db->dig); free(db->off); free(db->rng);
     free(db->move_off); free(db->n_moves); free(db->win_start); free(db->win_len); free(db->moves);
     free(db);
 }

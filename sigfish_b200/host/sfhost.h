@@ -111,7 +111,8 @@ typedef struct {
     aln_t *aln;
     char **out;
     /* packing scratch */
-    int64_t *sig_off;
+    int64_t *sig_off;   /* per-read sample counts */
+    int16_t **sig_ptr;  /* per-read signal buffers */
     float *dig, *off, *rng;
     int32_t shard_begin[SFHOST_MAX_GPUS + 1];
     /* --sam: winners' paths and window event boundaries */

@@ -166,6 +166,8 @@ def test_batch_slots_and_resubmit_are_deterministic():
     assert a.tobytes() == b.tobytes()
     ctx.resubmit(0)
     assert ctx.collect(0).tobytes() == b.tobytes()
+    ctx.submit_reads(1, sigs, sc)  # one pointer per read instead of one flat buffer
+    assert ctx.collect(1).tobytes() == b.tobytes()
     t = ctx.timing(0)
     assert t.dtw_launches == 1 and t.cells > 0 and t.dtw_ms > 0
     ctx.close()
