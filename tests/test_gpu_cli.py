@@ -45,7 +45,10 @@ def _inputs(tmp, case, fmt):
 
 
 def _run(cli, c, fa, reads, mf, extra=()):
-    cmd = [cli, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"])] + H.flags_to_cli(c["flags"]) + list(extra)
+    extra = list(extra)
+    if "--gpus" not in extra:  # the CLI takes every visible GPU by default; one is enough (and much faster to set up)
+        extra += ["--gpus", "1"]
+    cmd = [cli, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"])] + H.flags_to_cli(c["flags"]) + extra
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout, r.stderr
@@ -90,7 +93,7 @@ def test_cli_errors_like_the_reference(cli, tmp_path):
     for extra, msg in ((["--dtw-std"], "DTW is only available for RNA"), (["--invert"], "Inversion is only available for RNA"),
                        (["--full-ref"], "--full-ref is only available for RNA"), (["-p", "-1"], "DNA does not support auto query start"),
                        (["--pore", "r11"], "Pore model should be")):
-        r = subprocess.run([cli, "dtw", fa, reads, "--kmer-model", mf] + extra, capture_output=True, text=True)
+        r = subprocess.run([cli, "dtw", fa, reads, "--kmer-model", mf, "--gpus", "1"] + extra, capture_output=True, text=True)
         assert r.returncode != 0 and msg in r.stderr, (extra, r.stderr)
     r = subprocess.run([cli, "dtw", fa, reads], capture_output=True, text=True)
     assert r.returncode != 0 and "--kmer-model" in r.stderr
