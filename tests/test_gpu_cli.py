@@ -115,3 +115,30 @@ def test_cli_sam_is_byte_identical_to_reference(cli, tmp_path, case):
     strip = lambda t: "".join(l for l in t.splitlines(keepends=True) if not l.startswith("@PG"))
     assert strip(out) == strip(want)
     assert out.count("@PG\tID:sigfish") == 1
+
+
+def test_cli_c4_scale_matches_reference_binary(cli, tmp_path):
+    """BASELINE.json configs[3] shape through both command lines on the same files: one 1 Mb contig (R10 k=9,
+    both strands, 5e8 cells per read).  The unmodified reference binary (oracle/_ref/sigfish, ~0.3 s per read
+    on 16 cores) maps the first 16 reads; `sigfish-b200 dtw` maps 600 in several batches: the PAF of the common
+    reads must be byte-identical."""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    k = 9
+    mean, stdv = synth.make_model(k)
+    seq = synth.random_sequence(1_000_000, np.random.default_rng(1))
+    sigs, _ = synth.simulate_reads([seq], k, mean, 600, seed=4242, bases_per_read=450)
+    ids = [f"read_{i:06d}" for i in range(len(sigs))]
+    fa, mf = str(tmp_path / "ref.fa"), str(tmp_path / "model.txt")
+    synth.write_fasta(fa, ["chrS"], [seq])
+    synth.write_model_file(mf, k, mean, stdv)
+    synth.write_blow5(str(tmp_path / "all.blow5"), ids, sigs, kit="sqk-lsk114")
+    synth.write_blow5(str(tmp_path / "head.blow5"), ids[:16], sigs[:16], kit="sqk-lsk114")
+    r = subprocess.run([cli, "dtw", fa, str(tmp_path / "all.blow5"), "--kmer-model", mf, "--gpus", "1", "-K", "256"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "--pore r10 was set automatically" in r.stderr
+    want = H.run_ref(fa, str(tmp_path / "head.blow5"), mf, threads=os.cpu_count() or 8)
+    assert want.count("\n") == 16
+    assert "".join(r.stdout.splitlines(keepends=True)[:16]) == want
+    assert r.stdout.count("\n") == 600
