@@ -48,6 +48,9 @@ WORKLOAD = "C4: synthetic R10 DNA (k=9), reads x q=250 vs one 1 Mb contig, both 
 SASS_PER_STEP = 27.0
 ISSUE_SLOTS_PER_STEP = 35.0
 ROWS_PER_LANE = 8
+# DRAM traffic of one DTW launch from the committed `ncu --set full` capture (profiles/r01_ncu_summary.md:
+# dram__bytes_read.sum + dram__bytes_write.sum at 5920 reads); almost all of it is wavefront checkpoints
+NCU_DTW_TRAFFIC = {"reads": 5920, "bytes": 151.729408e6 + 3778.607e6}
 
 
 def make_workload(n_reads: int, seed: int, ref_len: int = REF_LEN):
@@ -295,7 +298,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "alu-issue", "kernel": "sf_dtw_score_kernel<8,false>",
                          "achieved": dtw_cells_per_s / 1e9, "peak": peak_cells / 1e9, "unit": "GCUPS",
-                         "frac": dtw_cells_per_s / peak_cells, "traffic": None,
+                         "frac": dtw_cells_per_s / peak_cells,
+                         "traffic": NCU_DTW_TRAFFIC["bytes"] if len(sigs) == NCU_DTW_TRAFFIC["reads"] else None,
+                         "traffic_note": "bytes per launch, ncu capture of this workload (profiles/r01_ncu_summary.md); "
+                                         "algorithmic HBM bytes are 0.016 B/cell (8 MB reference stream, L2 resident) "
+                                         "plus the wavefront checkpoints (0.66 MB/read)",
                          "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
                                         f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
                                         f"({SASS_PER_STEP:.0f} SASS per column, the 8 half-rate FMNMX3 counted twice)",
