@@ -676,7 +676,9 @@ void collect_db(core_t *core, db_t *db)
             db->too_short++;
         if (r->status & 16)
             db->prefix_fail++;
-        if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0)
+        /* no hit (only possible for degenerate queries, e.g. a constant signal whose z-score is NaN: the
+         * reference's behaviour is undefined there): print nothing */
+        if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0 || r->pos_st < 0 || r->pos_end < 0)
             continue;
         /* src/sigfish.c:969-985 */
         aln_t *a = &db->aln[i];

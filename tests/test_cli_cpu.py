@@ -1,0 +1,80 @@
+"""CPU-side behaviour of the `sigfish-b200` command line: everything that happens before a GPU is needed
+(usage, version, option validation in the reference's order) and the loud failure when there is no device."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from sigfish_b200 import build as B
+from sigfish_b200 import capi, synth
+
+
+@pytest.fixture(scope="module")
+def cli():
+    B.build_all()
+    return B.CLI
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    k = 5
+    mean, stdv = synth.make_model(k)
+    rng = np.random.default_rng(0)
+    seqs = [synth.random_sequence(900, rng)]
+    sigs, _ = synth.simulate_reads(seqs, k, mean, 2, seed=1, rna=True, bases_per_read=300)
+    fa, s5, mf = str(d / "r.fa"), str(d / "r.blow5"), str(d / "m.txt")
+    synth.write_fasta(fa, ["t1"], seqs)
+    synth.write_blow5(s5, ["a", "b"], sigs, rna=True)
+    synth.write_model_file(mf, k, mean, stdv)
+    return fa, s5, mf
+
+
+def run(cli, *args):
+    return subprocess.run([cli, *args], capture_output=True, text=True)
+
+
+def test_usage_version_help(cli):
+    r = run(cli)
+    assert r.returncode != 0 and "Usage: sigfish-b200 <command>" in r.stderr
+    r = run(cli, "--version")
+    assert r.returncode == 0 and r.stdout.startswith("sigfish ")
+    r = run(cli, "dtw", "--version")
+    assert r.returncode == 0 and r.stdout.startswith("sigfish ")
+    r = run(cli, "dtw", "-h")
+    assert r.returncode == 0 and "Usage: sigfish dtw [OPTIONS] genome.fa reads.blow5" in r.stdout
+    for opt in ("-K INT", "-B FLOAT", "--kmer-model", "--rna", "-q INT", "-p INT", "--dtw-std", "--invert", "--full-ref",
+                "--from-end", "--sam", "--pore", "--gpus"):
+        assert opt in r.stdout, opt
+    r = run(cli, "eval")
+    assert r.returncode != 0 and "Unrecognised command" in r.stderr
+
+
+def test_option_validation_precedes_everything(cli, files):
+    fa, s5, mf = files
+    cases = [(["-K", "0"], "Batch size should larger than 0"), (["-t", "0"], "Number of threads should larger than 0"),
+             (["-B", "0"], "Maximum number of bytes should be larger than 0"), (["-q", "-5"], "Query size should larger than 0"),
+             (["--gpus", "0"], "Number of GPUs should larger than 0"),
+             (["--rna", "-p", "-1", "--invert"], "Inversion is not compatible with auto query start"),
+             (["--rna", "-p", "-1", "--from-end"], "not compatible with auto query start"),
+             (["--dtw-std"], "DTW is only available for RNA")]  # the file IS RNA, but the check precedes detection
+    for extra, msg in cases:
+        r = run(cli, "dtw", fa, s5, "--kmer-model", mf, *extra)
+        assert r.returncode != 0 and msg in r.stderr, (extra, r.stderr[-400:])
+    r = run(cli, "dtw", fa, s5, "--kmer-model", mf, "--pore", "rna004", "-K", "0")  # accepted here (reference bug F6)
+    assert "Pore model should be" not in r.stderr
+
+
+def test_no_gpu_is_a_hard_error(cli, files):
+    if capi.lib().sfgpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    fa, s5, mf = files
+    r = run(cli, "dtw", fa, s5, "--kmer-model", mf)
+    assert r.returncode != 0
+    assert "no sm_100 (B200) GPU visible" in r.stderr and "no CPU path" in r.stderr
+    assert r.stdout == ""
+    # a missing model is reported before the device is looked for
+    r = run(cli, "dtw", fa, s5)
+    assert r.returncode != 0 and "--kmer-model" in r.stderr
