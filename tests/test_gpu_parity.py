@@ -441,3 +441,25 @@ def test_event_prefix_sums_inexact_fallback():
     assert_hit_equal(got, o, "inexact", 0, 250, 50)
     ref.close()
     ctx.close()
+
+
+def test_many_short_references_more_groups_than_lanes():
+    """load-balance shape of BASELINE.json configs[4]: many transcripts of <= 375 columns are packed into more
+    than 32 segment groups per read (the per-read merge then needs several groups per lane); --rna --invert"""
+    k = 5
+    lm = model(k)
+    rng = np.random.default_rng(31)
+    seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(380, 1500, size=1300)]
+    flags = H.F_RNA | H.F_INV
+    sigs, truth = synth.simulate_reads(seqs, k, lm, 6, seed=8, rna=True, bases_per_read=420)
+    sc = [synth.RNA_SCALING] * len(sigs)
+    ctx = capi.Context(lm, k, flags=flags)
+    ctx.set_ref(seqs)
+    assert ctx.ref_columns > 32 * 8192  # > 32 groups at the minimum group size... 
+    got = ctx.map_batch(sigs, sc)
+    ref = H.OracleRef(seqs, lm, k, flags, 250)
+    for i, s in enumerate(sigs):
+        o = H.orc_map(ref, s, sc[i]["digitisation"], sc[i]["offset"], sc[i]["range"], flags, 250, 50)
+        assert_hit_equal(got[i], o, ("many", i), flags, 250, 50)
+    ref.close()
+    ctx.close()
