@@ -455,7 +455,7 @@ def test_many_short_references_more_groups_than_lanes():
     sc = [synth.RNA_SCALING] * len(sigs)
     ctx = capi.Context(lm, k, flags=flags)
     ctx.set_ref(seqs)
-    assert ctx.ref_columns > 32 * 8192  # > 32 groups at the minimum group size... 
+    assert ctx.ref_columns > 32 * 8192  # ~64 groups of ~7.6 k columns (sfgpu.cu:layout_ref)
     got = ctx.map_batch(sigs, sc)
     ref = H.OracleRef(seqs, lm, k, flags, 250)
     for i, s in enumerate(sigs):
