@@ -565,9 +565,9 @@ int sfgpu_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess)
         return 0;
     int ok = 0;
-    for (int i = 0; i < n; i++) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10)
+    for (int i = 0; i < n; i++) { // attributes, not cudaGetDeviceProperties: the latter costs ~0.1 s per device
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10)
             ok++;
     }
     return ok;
@@ -594,8 +594,9 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         return fail(nullptr, SFGPU_ENODEV, "no CUDA device (this library has no CPU fallback)");
     if (opt->device < 0 || opt->device >= ndev)
         return fail(nullptr, SFGPU_EARG, "device %d out of range (%d present)", opt->device, ndev);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, opt->device) != cudaSuccess || prop.major != 10)
+    int cc_major = 0, n_sm = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, opt->device) != cudaSuccess || cc_major != 10 ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, opt->device) != cudaSuccess || n_sm <= 0)
         return fail(nullptr, SFGPU_ENODEV, "device %d is not an sm_100 GPU (kernels are built for sm_100a only)", opt->device);
 
     sfgpu_ctx *c = new (std::nothrow) sfgpu_ctx();
@@ -612,7 +613,7 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         c->ev_cap_a = 50 + opt->query_size + 4;
         c->ev_cap = c->ev_cap_a + opt->query_size + 4;
     }
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = n_sm;
     c->min_window = 2 * opt->query_size;
     if (opt->reserved[0] > 0)
         c->ck_min_cols = std::max(128, opt->reserved[0]);

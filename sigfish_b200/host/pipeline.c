@@ -146,6 +146,12 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
     char err[512];
     sf_verbosity = opt.verbosity;
 
+    const double t_init0 = sf_realtime();
+#define SF_STAGE(msg)                                                                                 \
+    do {                                                                                              \
+        if (sf_verbosity >= 5)                                                                        \
+            fprintf(stderr, "[init_core::%.3f] %s\n", sf_realtime() - t_init0, msg);                  \
+    } while (0)
     core->sf = sf_s5_open(slow5file, err, sizeof err);
     if (!core->sf) {
         SF_FATAL("Error opening SLOW5 file: %s", err);
@@ -175,8 +181,10 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
         SF_FATAL("%s", err);
     }
 
+    SF_STAGE("model read");
     /* GPUs */
     int ndev = sfgpu_device_count();
+    SF_STAGE("device count");
     if (ndev < 1) {
         SF_FATAL("%s", "no sm_100 (B200) GPU visible: this build has no CPU path");
     }
@@ -194,6 +202,7 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
     if (sf_fasta_read(fastafile, &fa, err, sizeof err)) {
         SF_FATAL("%s", err);
     }
+    SF_STAGE("FASTA read");
     refsynth_t *ref = (refsynth_t *)calloc(1, sizeof(refsynth_t));
     ref->num_ref = fa.num_ref;
     ref->ref_names = fa.names;
@@ -239,8 +248,10 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
         free(ia);
         free(tid);
     }
+    SF_STAGE("GPU contexts + resident reference");
     free(fa.bases);
     free(fa.off);
+#undef SF_STAGE
 
     core->opt = opt;
     core->realtime0 = realtime0;
