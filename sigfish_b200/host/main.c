@@ -1,6 +1,6 @@
 /* main.c -- entry of the `sigfish-b200` binary: `sigfish-b200 dtw [OPTIONS] genome.fa reads.blow5`.
- * Sub-command dispatch and the trailer lines follow reference src/main.c:64-102; only `dtw` exists
- * here (eval and the other sub-tools are outside the hot path). */
+ * Sub-command dispatch and the trailer lines follow reference src/main.c:64-102; `dtw` (the hot
+ * path) and `eval` (the scorer the reference's test scripts grade `dtw` output with) exist here. */
 #include <stdlib.h>
 #include <string.h>
 
@@ -10,7 +10,8 @@ static int usage(FILE *fp)
 {
     fprintf(fp, "Usage: sigfish-b200 <command> [options]\n\n");
     fprintf(fp, "command:\n");
-    fprintf(fp, "         dtw           map raw signal reads to a reference by subsequence DTW on B200 GPUs\n\n");
+    fprintf(fp, "         dtw           map raw signal reads to a reference by subsequence DTW on B200 GPUs\n");
+    fprintf(fp, "         eval          compare a test set of mappings (PAF) with a truth set\n\n");
     return fp == stdout ? EXIT_SUCCESS : EXIT_FAILURE;
 }
 
@@ -22,6 +23,8 @@ int main(int argc, char *argv[])
         return usage(stderr);
     if (!strcmp(argv[1], "dtw")) {
         ret = dtw_main(argc - 1, argv + 1);
+    } else if (!strcmp(argv[1], "eval")) {
+        ret = eval_main(argc - 1, argv + 1);
     } else if (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V")) {
         fprintf(stdout, "sigfish %s\n", SFHOST_VERSION);
         return EXIT_SUCCESS;

@@ -177,6 +177,9 @@ void sam_hdr_wr(const refsynth_t *ref);
 /* `sigfish dtw` command line (src/dtw_main.c) */
 int dtw_main(int argc, char *argv[]);
 
+/* `sigfish eval truth.paf test.paf` (src/eval.c) */
+int eval_main(int argc, char *argv[]);
+
 /* helpers shared by the sources of this directory */
 double sf_realtime(void);
 double sf_cputime(void);

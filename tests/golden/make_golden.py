@@ -134,6 +134,17 @@ CASES = {
 }
 
 
+# name -> (truth PAF, test PAF, options) for `sigfish eval`
+EVAL_CASES = {
+    "dna_synth48_vs_from_end": ("dna_synth48.paf", "dna_synth48_from_end.paf", []),
+    "rna_default_vs_full_ref": ("rna_sequin_default.paf", "rna_sequin_full_ref.paf", []),
+    "rna_default_vs_full_ref_tid_only": ("rna_sequin_default.paf", "rna_sequin_full_ref.paf", ["--tid-only"]),
+    "disjoint_read_sets": ("dna_short_reads.paf", "dna_synth48.paf", []),
+    "crafted": ("crafted_truth.paf", "crafted_test.paf", []),
+    "crafted_no_secondary": ("crafted_truth.paf", "crafted_test.paf", ["--secondary", "no"]),
+    "crafted_tid_only": ("crafted_truth.paf", "crafted_test.paf", ["--tid-only"]),
+}
+
 SAM_CASES = ["dna_sp1_default", "dna_sp1_from_end", "dna_synth48", "dna_multi_contig", "dna_short_reads", "dna_r10_k9",
              "rna_sequin_default", "rna_sequin_invert", "rna_sequin_full_ref", "rna_sequin_q500_auto",
              "rna_tail24_auto", "rna_synth32"]
@@ -223,6 +234,41 @@ def main():
         with open(os.path.join(HERE, "sam", case + ".sam"), "w") as f:
             f.write(sam)
         print("sam", case, sam.count("\n"), "lines")
+
+    # 3c. `sigfish eval` reports (stdout) for truth/test pairs made of the golden PAFs plus one crafted pair
+    #     with secondary records, several truth mappings per read and reads missing from the truth set
+    import subprocess
+    ev = os.path.join(HERE, "eval")
+    os.makedirs(ev, exist_ok=True)
+    rows = open(os.path.join(HERE, "paf", "dna_synth48.paf")).read().splitlines()
+    crafted_truth, crafted_test = [], []
+    for i, r in enumerate(rows[:30]):
+        f = r.split("\t")
+        crafted_truth.append("\t".join(f[:12] + ["tp:A:P"]))
+        if i % 3 == 0:  # a secondary truth mapping somewhere else
+            g = list(f)
+            g[7], g[8] = str(int(f[7]) + 5000), str(int(f[8]) + 5000)
+            crafted_truth.append("\t".join(g[:12] + ["tp:A:S"]))
+        t = list(f)
+        if i % 4 == 1:   # shifted by 5000: correct only against the secondary truth record
+            t[7], t[8] = str(int(f[7]) + 5000 + 40), str(int(f[8]) + 5000 - 30)
+        elif i % 4 == 2:  # wrong strand
+            t[4] = "-" if f[4] == "+" else "+"
+        elif i % 4 == 3:  # start off by 150, end off by 60: still correct (min of the two)
+            t[7], t[8] = str(int(f[7]) + 150), str(int(f[8]) + 60)
+        t[11] = str((i * 7) % 61)
+        crafted_test.append("\t".join(t[:12] + ["tp:A:P"]))
+    for r in rows[40:44]:  # reads the truth set does not have
+        crafted_test.append(r)
+    open(os.path.join(ev, "crafted_truth.paf"), "w").write("\n".join(crafted_truth) + "\n")
+    open(os.path.join(ev, "crafted_test.paf"), "w").write("\n".join(crafted_test) + "\n")
+    pafd = os.path.join(HERE, "paf")
+    for name, (truth, test, opts) in EVAL_CASES.items():
+        tp = os.path.join(ev, truth) if truth.startswith("crafted") else os.path.join(pafd, truth)
+        sp = os.path.join(ev, test) if test.startswith("crafted") else os.path.join(pafd, test)
+        r = subprocess.run([H.REF_BIN, "eval"] + opts + [tp, sp], capture_output=True, text=True, check=True)
+        open(os.path.join(ev, name + ".txt"), "w").write(r.stdout)
+        print("eval", name, r.stdout.count("\n"), "lines")
 
     # 4. event tables straight from the reference's getevents()
     for name, rna in (("sp1_dna", False), ("sequin_rna", True), ("synth_dna_short", False)):

@@ -78,3 +78,40 @@ def test_no_gpu_is_a_hard_error(cli, files):
     # a missing model is reported before the device is looked for
     r = run(cli, "dtw", fa, s5)
     assert r.returncode != 0 and "--kmer-model" in r.stderr
+
+
+EVAL = os.path.join(H.GOLDEN, "eval")
+EVAL_CASES = {
+    "dna_synth48_vs_from_end": ("dna_synth48.paf", "dna_synth48_from_end.paf", []),
+    "rna_default_vs_full_ref": ("rna_sequin_default.paf", "rna_sequin_full_ref.paf", []),
+    "rna_default_vs_full_ref_tid_only": ("rna_sequin_default.paf", "rna_sequin_full_ref.paf", ["--tid-only"]),
+    "disjoint_read_sets": ("dna_short_reads.paf", "dna_synth48.paf", []),
+    "crafted": ("crafted_truth.paf", "crafted_test.paf", []),
+    "crafted_no_secondary": ("crafted_truth.paf", "crafted_test.paf", ["--secondary", "no"]),
+    "crafted_tid_only": ("crafted_truth.paf", "crafted_test.paf", ["--tid-only"]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(EVAL_CASES))
+def test_eval_report_matches_reference_golden(cli, case):
+    """`sigfish-b200 eval` prints the report the reference's `sigfish eval` printed for the same PAF pair
+    (tests/golden/eval/*.txt, made by tests/golden/make_golden.py)"""
+    truth, test, opts = EVAL_CASES[case]
+    loc = lambda f: os.path.join(EVAL, f) if f.startswith("crafted") else os.path.join(H.GOLDEN, "paf", f)
+    r = run(cli, "eval", *opts, loc(truth), loc(test))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(EVAL, case + ".txt")).read()
+    assert "Total mappings in testset" in r.stderr
+
+
+def test_eval_usage_and_errors(cli, tmp_path):
+    r = run(cli, "eval")
+    assert r.returncode != 0 and "Usage: sigfish eval truth.paf test.paf" in r.stderr
+    r = run(cli, "eval", "-h")
+    assert r.returncode == 0 and "--tid-only" in r.stdout
+    r = run(cli, "eval", str(tmp_path / "nope.paf"), str(tmp_path / "nope2.paf"))
+    assert r.returncode != 0 and "cannot open" in r.stderr
+    bad = tmp_path / "bad.paf"
+    bad.write_text("r1\t100\t0\t50\t+\tchr\n")
+    r = run(cli, "eval", str(bad), str(bad))
+    assert r.returncode != 0 and "malformed PAF" in r.stderr
