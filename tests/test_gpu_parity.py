@@ -463,3 +463,44 @@ def test_many_short_references_more_groups_than_lanes():
         assert_hit_equal(got[i], o, ("many", i), flags, 250, 50)
     ref.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("q", [10, 40, 90, 128, 150, 180, 200, 256, 320, 380, 512, 600, 760, 1000, 1024])
+def test_dtw_every_register_tile_height(q):
+    """one case per template instantiation of the DTW / trace kernels (R = 1,2,3,4,5,6,7,8,10,12,16,20,24,32):
+    subsequence and standard DTW, full-length and ragged queries, checkpoints on"""
+    rng = np.random.default_rng(5000 + q)
+    lens = [int(x) for x in rng.integers(1, 700, size=4)] + [2 * q + 37, 2500]
+    fwd = _rand_arrays(rng, lens, 2)
+    rev = _rand_arrays(rng, lens, 2)
+    qlens = [q, q, max(1, q - 1), max(1, (2 * q) // 3), min(q, 25)]
+    queries = _rand_arrays(rng, qlens, 2)
+    oref = H.OracleEventRef(fwd, rev)
+    ctx = capi.Context(model(5), 5, query_size=q, ck_min_cols=256, min_window=8)
+    ctx.set_ref_events(fwd, rev)
+    got = ctx.align_queries(queries)
+    for i, x in enumerate(queries):
+        o = oref.align(x, 0)
+        g = got[i]
+        assert (g["rid"], "+-"[g["strand"]]) == (o.rid, o.strand.decode()), (q, i)
+        assert bits(g["score"]) == bits(o.score) and bits(g["score2"]) == bits(o.score2), (q, i)
+        assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), (q, i)
+    ctx.close()
+    oref.close()
+    oref = H.OracleEventRef(fwd, None)
+    ctx = capi.Context(model(5), 5, flags=H.F_RNA | H.F_DTW, query_size=q, ck_min_cols=256, min_window=8)
+    ctx.set_ref_events(fwd, None)
+    got = ctx.align_queries(queries)
+    for i, x in enumerate(queries):
+        o = oref.align(x[::-1].copy(), H.F_RNA | H.F_DTW)
+        g = got[i]
+        assert g["rid"] == o.rid, (q, i)
+        assert bits(g["score"]) == bits(o.score) and bits(g["score2"]) == bits(o.score2), (q, i)
+        assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), (q, i)
+    ctx.close()
+    oref.close()
+
+
+def test_query_size_limit_is_reported():
+    with pytest.raises(capi.SfgpuError, match="1024"):
+        capi.Context(model(5), 5, query_size=1025)
