@@ -149,11 +149,15 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
             if (RQ >= 0) {
                 sf_sts2(last_s + 8 * s, keepA, keepB);
             } else {
+                if (R % 2 == 0) { // 16-byte stores need (s*R + r) even
 #pragma unroll
-                for (int r = 0; r + 1 < R; r += 2)
-                    sf_sts4(last_s + 8 * (s * R + r), allA[r], L[r], allA[r + 1], L[r + 1]);
-                if (R & 1)
-                    sf_sts2(last_s + 8 * (s * R + R - 1), allA[R - 1], L[R - 1]);
+                    for (int r = 0; r < R; r += 2)
+                        sf_sts4(last_s + 8 * (s * R + r), allA[r], L[r], allA[r + 1], L[r + 1]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        sf_sts2(last_s + 8 * (s * R + r), allA[r], L[r]);
+                }
             }
         }
     }

@@ -316,7 +316,7 @@ def test_auto_query_start_rna004_parameter_set():
     ctx.close()
 
 
-@pytest.mark.parametrize("q", [33, 250, 300])
+@pytest.mark.parametrize("q", [33, 90, 200, 250, 300, 600])
 @pytest.mark.parametrize("quant", [0, 2])
 def test_warping_paths_match_oracle_backtrack(q, quant):
     """--sam support: sfgpu_collect_paths() must return exactly the path subsequence_path() finds in the full
