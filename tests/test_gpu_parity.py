@@ -504,3 +504,73 @@ def test_dtw_every_register_tile_height(q):
 def test_query_size_limit_is_reported():
     with pytest.raises(capi.SfgpuError, match="1024"):
         capi.Context(model(5), 5, query_size=1025)
+
+
+def test_auto_query_start_on_truncated_reads():
+    """-p -1 edge cases: reads cut inside the adaptor, inside the poly-A tail, right after it (start found but
+    fewer than q / fewer than 25 events left: too short / ignored), reads shorter than the 2000-sample window
+    of the adaptor finder, plus transcripts shorter than 1.5*q in the reference"""
+    c = CASES["rna_tail24_auto"]
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    k, q = c["k"], c["q"]
+    rng = np.random.default_rng(17)
+    seqs = [synth.random_sequence(int(n), rng) for n in (300, 5, 60, 900, 379, 380, 2000)]
+    cut = []
+    for i, s in enumerate(sigs[:12]):
+        for n in (1500, 2001, 3500, 5200, 6500, 7600, 9000, 12000):
+            if n < len(s):
+                cut.append(s[:n])
+    scs = [synth.RNA_SCALING] * len(cut)
+    ctx = capi.Context(model(k), k, flags=H.F_RNA, query_size=q, prefix_size=-1)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(cut, scs)
+    ref = H.OracleRef(seqs, model(k), k, H.F_RNA, q)
+    seen = set()
+    for i, s in enumerate(cut):
+        o = H.orc_map(ref, s, scs[i]["digitisation"], scs[i]["offset"], scs[i]["range"], H.F_RNA, q, -1)
+        assert_hit_equal(got[i], o, ("cut", i, len(s)), H.F_RNA, q, -1)
+        seen.add((bool(o.mapped), o.status))
+    assert len(seen) >= 3, seen  # mapped / too short / ignored / prefix-fail combinations all occurred
+    ref.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_match_oracle(seed):
+    """seeded fuzz over the option space: chemistry, flag combinations the CLI accepts, q, p, contig counts and
+    lengths (down to a single k-mer), read lengths from 'ignored' to several thousand events"""
+    rng = np.random.default_rng(9000 + seed)
+    rna = bool(rng.integers(0, 2))
+    k = 5 if rna else int(rng.choice([6, 9]))
+    flags = 0
+    if rna:
+        flags = H.F_RNA
+        flags |= int(rng.choice([0, H.F_DTW, H.F_INV, H.F_REF, H.F_DTW | H.F_REF, H.F_INV | H.F_REF]))
+    if rng.integers(0, 3) == 0 and not (flags & H.F_INV and False):
+        flags |= H.F_END
+    q = int(rng.choice([25, 60, 97, 130, 250, 250, 333, 420]))
+    p = int(rng.choice([0, 10, 50, 50, 120]))
+    n_contig = int(rng.integers(1, 7))
+    seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(k, 4000, size=n_contig)]
+    seqs[0] = synth.random_sequence(int(rng.integers(600, 5000)), rng)
+    lm = model(k)
+    sigs = []
+    scs = []
+    for r in range(8):
+        nb = int(rng.choice([30, 80, 150, 300, 450, 700]))
+        s, _ = synth.simulate_reads([seqs[0]], k, lm, 1, seed=int(rng.integers(1 << 30)), rna=rna, bases_per_read=nb,
+                                    min_samples=600)
+        sigs.append(s[0])
+        base = synth.RNA_SCALING if rna else synth.DNA_SCALING
+        scs.append(dict(base, offset=float(base["offset"] + rng.integers(-20, 20)), range=float(base["range"] * rng.uniform(0.9, 1.1))))
+    ctx = capi.Context(lm, k, flags=flags, query_size=q, prefix_size=p)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, scs)
+    ref = H.OracleRef(seqs, lm, k, flags, q)
+    for i, s in enumerate(sigs):
+        o = H.orc_map(ref, s, scs[i]["digitisation"], scs[i]["offset"], scs[i]["range"], flags, q, p)
+        if o.mapped and (np.isnan(o.score) or np.isnan(o.score2)):
+            continue  # a degenerate reference (single-column contig z-scores to NaN): undefined in the reference
+        assert_hit_equal(got[i], o, (seed, i, flags, q, p), flags, q, p)
+    ref.close()
+    ctx.close()
