@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/sfgpu.h"
@@ -223,24 +224,22 @@ template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cuda
     return cudaGetLastError();
 }
 
+// Calls f(integral_constant<int, R>, bool_constant<STD>) for the instantiated register-tile height equal to
+// `rows` (kRows) and the recurrence variant; returns false when `rows` is not instantiated.
+template <int... Rs> struct sf_row_list {};
+using sf_rows = sf_row_list<1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32>;
+
+template <typename F, int... Rs> bool dispatch_rows(int rows, bool std_dtw, F &&f, sf_row_list<Rs...>)
+{
+    return ((rows == Rs && (std_dtw ? (f(std::integral_constant<int, Rs>{}, std::true_type{}), true)
+                                    : (f(std::integral_constant<int, Rs>{}, std::false_type{}), true))) || ...);
+}
 #define SF_DISPATCH_R(R_, STD_, EXPR)                                                             \
-    switch (R_) {                                                                                 \
-    case 1: { constexpr int R = 1; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 2: { constexpr int R = 2; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 3: { constexpr int R = 3; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 4: { constexpr int R = 4; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 5: { constexpr int R = 5; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 6: { constexpr int R = 6; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 7: { constexpr int R = 7; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 8: { constexpr int R = 8; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 10: { constexpr int R = 10; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 12: { constexpr int R = 12; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 16: { constexpr int R = 16; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 20: { constexpr int R = 20; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 24: { constexpr int R = 24; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    case 32: { constexpr int R = 32; if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } } break; \
-    default: break;                                                                               \
-    }
+    dispatch_rows((R_), (STD_), [&](auto r_tag_, auto std_tag_) {                                 \
+        constexpr int R = decltype(r_tag_)::value;                                                \
+        constexpr bool STD = decltype(std_tag_)::value;                                           \
+        EXPR;                                                                                     \
+    }, sf_rows{})
 
 // the device stages of one batch, on the slot's stream
 int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
