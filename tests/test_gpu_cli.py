@@ -88,6 +88,21 @@ def test_cli_read_sharding_over_gpus(cli, tmp_path):
         assert f"on {g} GPU(s)" in err
 
 
+def test_cli_read_sharding_sam_and_auto_start(cli, tmp_path):
+    """the per-shard path / window-event buffers of --sam and the -p -1 kernels with reads split over GPUs"""
+    n = capi.lib().sfgpu_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    strip = lambda t: "".join(l for l in t.splitlines(keepends=True) if not l.startswith("@PG"))
+    for case in ("rna_tail24_auto", "dna_synth48"):
+        c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+        want = open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()
+        out, _ = _run(cli, c, fa, reads, mf, ["--sam", "--gpus", "2", "-K", "9"])
+        assert strip(out) == strip(want), case
+        out, _ = _run(cli, c, fa, reads, mf, ["--gpus", "2"])
+        assert out == open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read(), case
+
+
 def test_cli_errors_like_the_reference(cli, tmp_path):
     c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "slow5")
     for extra, msg in ((["--dtw-std"], "DTW is only available for RNA"), (["--invert"], "Inversion is only available for RNA"),
