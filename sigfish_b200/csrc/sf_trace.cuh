@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
 
     // The pass uses the score kernel's macro-steps (two columns per lane per step: lane l is on columns
     // 2(T-l), 2(T-l)+1 at macro-step T) so that its checkpoints can be resumed as they are.
-    for (int attempt = 0; attempt < 64; attempt++) {
+    // Terminates: every retry restarts from a strictly earlier checkpoint (ck_limit shrinks), and the restart at
+    // the segment's sentinel always resolves.
+    for (;;) {
         // choose the restart: latest checkpoint k (< ck_limit) whose whole front lies at least
         // min_window columns before the target and after the segment's sentinel; else the sentinel.
         // Checkpoint k holds the state after macro-step T_k = 32*(k+1)*ck_every - 1: lane l's rows at
