@@ -574,3 +574,46 @@ def test_random_configurations_match_oracle(seed):
         assert_hit_equal(got[i], o, (seed, i, flags, q, p), flags, q, p)
     ref.close()
     ctx.close()
+
+
+def test_abi_misuse_is_reported_not_crashed():
+    """error convention of include/sfgpu.h: negative code + text, no abort, context still usable"""
+    import ctypes as C
+    L = capi.lib()
+    k = 6
+    rng = np.random.default_rng(2)
+    seqs = [synth.random_sequence(2000, rng)]
+    sigs, _ = synth.simulate_reads(seqs, k, model(k), 3, seed=3, bases_per_read=400)
+    sc = [synth.DNA_SCALING] * 3
+    ctx = capi.Context(model(k), k)
+    with pytest.raises(capi.SfgpuError, match="before sfgpu_set_ref"):
+        ctx.submit(0, *ctx.pack(sigs, sc))
+    ctx.set_ref(seqs)
+    res = np.zeros(4, dtype=capi.RESULT_DTYPE)
+    assert L.sfgpu_collect(ctx._h, 0, res.ctypes.data_as(C.c_void_p)) == -4  # nothing submitted
+    assert L.sfgpu_collect(ctx._h, 7, res.ctypes.data_as(C.c_void_p)) == -2  # bad slot
+    assert L.sfgpu_resubmit(ctx._h, 1) == -4
+    with pytest.raises(capi.SfgpuError, match="no such"):
+        ctx.ref_events(3, 0)
+    with pytest.raises(capi.SfgpuError, match="contig 0 has 3 bases"):
+        ctx.set_ref([b"ACG"])
+    ctx.set_ref(seqs)  # still usable after the failed call
+    good = ctx.map_batch(sigs, sc)
+    assert (good["qlen"] == 250).all()
+    with pytest.raises(capi.SfgpuError, match="SFGPU_SAM"):
+        ctx.collect_paths(0, good)
+    with pytest.raises(capi.SfgpuError, match="qlen"):
+        ctx.submit_queries(0, [np.zeros(300, np.float32)])
+    ctx.close()
+    sam = capi.Context(model(k), k, flags=capi.SFGPU_SAM)
+    sam.set_ref(seqs)
+    r = sam.map_batch(sigs, sc)
+    off = np.zeros(4, dtype=np.int64)  # no room for any move
+    mv = np.zeros(8, np.uint8); nm = np.zeros(3, np.int32)
+    es = np.zeros(3 * 250, np.uint64); el = np.zeros(3 * 250, np.float32)
+    rc = L.sfgpu_collect_paths(sam._h, 0, off.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p),
+                               nm.ctypes.data_as(C.c_void_p), es.ctypes.data_as(C.c_void_p), el.ctypes.data_as(C.c_void_p))
+    assert rc == -2 and b"move buffer" in L.sfgpu_strerror(sam._h)
+    paths, _, _ = sam.collect_paths(0, r)  # and the proper call still works afterwards
+    assert all(p is not None for p in paths)
+    sam.close()
