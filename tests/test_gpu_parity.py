@@ -593,8 +593,9 @@ def test_abi_misuse_is_reported_not_crashed():
     assert L.sfgpu_collect(ctx._h, 0, res.ctypes.data_as(C.c_void_p)) == -4  # nothing submitted
     assert L.sfgpu_collect(ctx._h, 7, res.ctypes.data_as(C.c_void_p)) == -2  # bad slot
     assert L.sfgpu_resubmit(ctx._h, 1) == -4
-    with pytest.raises(capi.SfgpuError, match="no such"):
-        ctx.ref_events(3, 0)
+    buf = np.zeros(16, np.float32)
+    assert L.sfgpu_ref_events(ctx._h, 3, 0, buf.ctypes.data_as(C.c_void_p), 16) == -2  # no such contig
+    assert L.sfgpu_ref_events(ctx._h, 0, 0, buf.ctypes.data_as(C.c_void_p), 16) == -2  # buffer too small
     with pytest.raises(capi.SfgpuError, match="contig 0 has 3 bases"):
         ctx.set_ref([b"ACG"])
     ctx.set_ref(seqs)  # still usable after the failed call
