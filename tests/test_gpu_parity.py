@@ -603,8 +603,10 @@ def test_abi_misuse_is_reported_not_crashed():
     assert (good["qlen"] == 250).all()
     with pytest.raises(capi.SfgpuError, match="SFGPU_SAM"):
         ctx.collect_paths(0, good)
-    with pytest.raises(capi.SfgpuError, match="qlen"):
-        ctx.submit_queries(0, [np.zeros(300, np.float32)])
+    qbuf = np.zeros(250, np.float32)
+    qlen = np.array([300], np.int32)  # longer than query_size
+    assert L.sfgpu_submit_queries(ctx._h, 0, 1, qbuf.ctypes.data_as(C.c_void_p), qlen.ctypes.data_as(C.c_void_p)) == -2
+    assert b"qlen" in L.sfgpu_strerror(ctx._h)
     ctx.close()
     sam = capi.Context(model(k), k, flags=capi.SFGPU_SAM)
     sam.set_ref(seqs)
