@@ -138,18 +138,18 @@ def test_mapping_matches_oracle_on_golden_cases(case):
     names, seqs = H.read_fasta(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"))
     ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
     k, flags, q, p = c["k"], c["flags"], c["q"], c["p"]
-    ctx = capi.Context(model(k), k, flags=flags, query_size=q, prefix_size=p)
-    ctx.set_ref(seqs)
-    got = ctx.map_batch(sigs, sc)
     ref = H.OracleRef(seqs, model(k), k, flags, q)
-    rows = 0
-    for i, (s, cc) in enumerate(zip(sigs, sc)):
-        o = H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], flags, q, p)
-        assert_hit_equal(got[i], o, (case, i), flags, q, p)
-        rows += int(o.mapped)
-    assert rows == c["rows"]
+    want = [H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], flags, q, p) for s, cc in zip(sigs, sc)]
+    assert sum(int(o.mapped) for o in want) == c["rows"]
+    # both event-detection schedules: split (throughput kernel + lane-per-read detector) and fused
+    for fused in (False, True):
+        ctx = capi.Context(model(k), k, flags=flags, query_size=q, prefix_size=p, fused_events=fused)
+        ctx.set_ref(seqs)
+        got = ctx.map_batch(sigs, sc)
+        for i, o in enumerate(want):
+            assert_hit_equal(got[i], o, (case, i, fused), flags, q, p)
+        ctx.close()
     ref.close()
-    ctx.close()
 
 
 def test_batch_slots_and_resubmit_are_deterministic():
@@ -620,3 +620,30 @@ def test_abi_misuse_is_reported_not_crashed():
     paths, _, _ = sam.collect_paths(0, r)  # and the proper call still works afterwards
     assert all(p is not None for p in paths)
     sam.close()
+
+
+def test_split_event_schedule_falls_back_for_slow_reads():
+    """reads translocating so slowly that p+q events need more samples than the split schedule covers (n0) are
+    flagged by the detector kernel and redone by the fused kernel; mixed with ordinary reads in one batch"""
+    k = 6
+    lm = model(k)
+    rng = np.random.default_rng(41)
+    seqs = [synth.random_sequence(5000, rng)]
+    ranks_ = synth.kmer_ranks(seqs[0], k)
+    sigs = []
+    for i in range(10):
+        st = int(rng.integers(0, len(ranks_) - 500))
+        lv = lm[ranks_[st:st + 450]]
+        slow = i % 2 == 0
+        sigs.append(synth.simulate_read(lv, rng, synth.DNA_SCALING, mean_extra_dwell=45.0 if slow else 8.0, min_dwell=12 if slow else 2))
+    sc = [synth.DNA_SCALING] * len(sigs)
+    assert max(len(s) for s in sigs) > 3 * 4352
+    ref = H.OracleRef(seqs, lm, k, 0, 250)
+    ctx = capi.Context(lm, k)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    for i, s in enumerate(sigs):
+        o = H.orc_map(ref, s, 8192.0, 10.0, 1402.882, 0, 250, 50)
+        assert_hit_equal(got[i], o, ("slow", i), 0, 250, 50)
+    ref.close()
+    ctx.close()
