@@ -53,9 +53,6 @@ struct sf_slot {
     float *d_ev_mean = nullptr, *d_ev_len = nullptr;
     float *d_queries = nullptr;
     int64_t *d_polya = nullptr;
-    float2 *d_tt = nullptr;          // split event schedule: t-statistics / prefix sums / per-read flags
-    double *d_ss = nullptr;
-    int32_t *d_rflags = nullptr;
     uint64_t *d_win_start = nullptr; // --sam only
     float *d_win_len = nullptr;
     sf_readinfo *d_info = nullptr;
@@ -76,7 +73,6 @@ struct sf_slot {
 struct sfgpu_ctx {
     sfgpu_opt_t opt;
     int R = 0, q_cap = 0, ev_cap = 0, ev_cap_a = 0;
-    int ev_n0 = 0; // samples per read covered by the split event schedule (0: fused kernel only)
     int sm_count = 0;
     float *d_level_mean = nullptr;
     // reference
@@ -149,7 +145,6 @@ void slot_free_buffers(sf_slot &s)
     dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
     dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
-    dfree(s.d_tt); dfree(s.d_ss); dfree(s.d_rflags);
     s.cap_reads = 0;
     s.cap_samples = 0;
 }
@@ -170,7 +165,6 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
         dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
-        dfree(s.d_tt); dfree(s.d_ss); dfree(s.d_rflags);
         s.cap_reads = 0;
         const size_t n = (size_t)cap;
         SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
@@ -189,11 +183,6 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
             SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)sf_ckpt_floats(c->R)));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
         SF_CUDA(c, cudaMalloc(&s.d_polya, sizeof(int64_t) * n));
-        SF_CUDA(c, cudaMalloc(&s.d_rflags, sizeof(int32_t) * n));
-        if (c->ev_n0 > 0) {
-            SF_CUDA(c, cudaMalloc(&s.d_tt, sizeof(float2) * n * c->ev_n0));
-            SF_CUDA(c, cudaMalloc(&s.d_ss, sizeof(double) * n * (c->ev_n0 + 1)));
-        }
         if (c->opt.flags & SFGPU_SAM) {
             SF_CUDA(c, cudaMalloc(&s.d_win_start, sizeof(uint64_t) * n * c->q_cap));
             SF_CUDA(c, cudaMalloc(&s.d_win_len, sizeof(float) * n * c->q_cap));
@@ -310,21 +299,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
         }
-        ea.n0 = c->ev_n0;
-        ea.tt = s.d_tt;
-        ea.ss = s.d_ss;
-        ea.rflags = s.d_rflags;
-        ea.only_flagged = 0;
-        const int ev_grid = (n + SF_EV_READS_PER_BLOCK - 1) / SF_EV_READS_PER_BLOCK;
-        if (c->ev_n0 > 0) {
-            sf_tstat_kernel<<<ev_grid, SF_EV_THREADS, 0, st>>>(ea);
-            SF_CUDA(c, cudaGetLastError());
-            sf_detect_kernel<<<(n + 31) / 32, 32, 0, st>>>(ea);
-            SF_CUDA(c, cudaGetLastError());
-            ea.only_flagged = 1; // reads whose window lies beyond the first n0 samples
-            s.timing.other_launches += 2;
-        }
-        sf_events_kernel<<<ev_grid, SF_EV_THREADS, 0, st>>>(ea);
+        sf_events_kernel<<<(n + SF_EV_READS_PER_BLOCK - 1) / SF_EV_READS_PER_BLOCK, SF_EV_THREADS, 0, st>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         s.timing.other_launches++;
     }
@@ -638,15 +613,6 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         c->ev_cap = c->ev_cap_a + opt->query_size + 4;
     }
     c->sm_count = n_sm;
-    // Split event schedule (throughput kernel + lane-per-read detector) when the query window starts at a fixed
-    // event offset from the read start: p + q events need about 9 (DNA) / 20 (RNA) samples each; reads that need
-    // more fall back to the fused kernel.  --from-end and the automatic start need the whole read: fused only.
-    if (opt->prefix_size >= 0 && !(opt->flags & SFGPU_END) && opt->reserved[2] == 0) {
-        const int64_t per_event = (opt->flags & SFGPU_RNA) ? 28 : 14;
-        int64_t want = (int64_t)(opt->prefix_size + opt->query_size) * per_event;
-        want = std::max<int64_t>(1024, std::min<int64_t>(want, 65536));
-        c->ev_n0 = (int)((want + SF_EV_TILE - 1) / SF_EV_TILE * SF_EV_TILE);
-    }
     c->min_window = 2 * opt->query_size;
     if (opt->reserved[0] > 0)
         c->ck_min_cols = std::max(128, opt->reserved[0]);
@@ -1154,11 +1120,6 @@ int64_t sfgpu_event_table(sfgpu_ctx *c, const int16_t *signal, int64_t n_samples
         ea.cap_a = 0;
         ea.win_start = nullptr;
         ea.win_len = nullptr;
-        ea.n0 = 0;
-        ea.tt = nullptr;
-        ea.ss = nullptr;
-        ea.rflags = nullptr;
-        ea.only_flagged = 0;
         sf_events_kernel<<<1, SF_EV_THREADS>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         SF_CUDA(c, cudaDeviceSynchronize());

@@ -141,14 +141,12 @@ def test_mapping_matches_oracle_on_golden_cases(case):
     ref = H.OracleRef(seqs, model(k), k, flags, q)
     want = [H.orc_map(ref, s, cc["digitisation"], cc["offset"], cc["range"], flags, q, p) for s, cc in zip(sigs, sc)]
     assert sum(int(o.mapped) for o in want) == c["rows"]
-    # both event-detection schedules: split (throughput kernel + lane-per-read detector) and fused
-    for fused in (False, True):
-        ctx = capi.Context(model(k), k, flags=flags, query_size=q, prefix_size=p, fused_events=fused)
-        ctx.set_ref(seqs)
-        got = ctx.map_batch(sigs, sc)
-        for i, o in enumerate(want):
-            assert_hit_equal(got[i], o, (case, i, fused), flags, q, p)
-        ctx.close()
+    ctx = capi.Context(model(k), k, flags=flags, query_size=q, prefix_size=p)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    for i, o in enumerate(want):
+        assert_hit_equal(got[i], o, (case, i), flags, q, p)
+    ctx.close()
     ref.close()
 
 
@@ -622,9 +620,9 @@ def test_abi_misuse_is_reported_not_crashed():
     sam.close()
 
 
-def test_split_event_schedule_falls_back_for_slow_reads():
-    """reads translocating so slowly that p+q events need more samples than the split schedule covers (n0) are
-    flagged by the detector kernel and redone by the fused kernel; mixed with ordinary reads in one batch"""
+def test_slow_and_fast_reads_in_one_batch():
+    """reads translocating five times slower than the others (p+q events spread over > 13 k samples, many tiles
+    of the event kernel) mixed with ordinary reads in one batch"""
     k = 6
     lm = model(k)
     rng = np.random.default_rng(41)
