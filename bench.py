@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=0,
-                    help="reads per GPU per step (0: two full waves of DTW tasks, sfgpu_wave_reads(); 5920 on a 148-SM B200)")
+                    help="reads per GPU per step (0: four full waves of DTW tasks, 4 x sfgpu_wave_reads() = 11840 on a 148-SM B200)")
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU baseline sample (0: one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,8 +210,9 @@ def main():
     seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
     ctx = capi.Context(mean, KMER, flags=0, query_size=Q, prefix_size=P, device=local, n_slots=2)
     ctx.set_ref([seq])
-    # a task (one read x one strand of the 1 Mb contig) runs ~150 ms, so the batch is sized to whole waves
-    n_reads = args.reads if args.reads > 0 else 2 * ctx.wave_reads
+    # a task (one read x one strand of the 1 Mb contig) runs ~190 ms, so the batch is sized to whole waves of
+    # resident warps; four waves per step (measured per-wave time: 1 wave 197 ms, 2: 209, 3: 196, 4: 193, 6: 191, 8: 194)
+    n_reads = args.reads if args.reads > 0 else 4 * ctx.wave_reads
     sigs, _ = synth.simulate_reads([seq], KMER, mean, n_reads, seed=100 + rank, bases_per_read=450)
     sc = [synth.DNA_SCALING] * len(sigs)
     packed = ctx.pack(sigs, sc)
@@ -288,7 +289,7 @@ def main():
             "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": len(sigs), "query_size": Q, "prefix_size": P,
                        "kmer": KMER, "ref_columns": int(ref_cols), "cells_per_step_per_gpu": cells,
                        "samples_per_step_per_gpu": int(sum(len(s) for s in sigs)), "mapped_reads": mapped,
-                       "batch": "two full waves of (read, strand) DTW tasks per step (sfgpu_wave_reads)" if args.reads <= 0 else "--reads",
+                       "batch": "four full waves of (read, strand) DTW tasks per step (4 x sfgpu_wave_reads)" if args.reads <= 0 else "--reads",
                        "l2": "256 MB buffer written between timed iterations (L2 flush)",
                        "parallelism": f"reads sharded over {world} GPU(s), reference replicated, no collective"},
             "stage_ms": {"events": evt_ms, "dtw": dtw_ms, "merge_trace": trc_ms, "wall_per_step_incl_flush": wall_step},
@@ -299,8 +300,9 @@ def main():
             "roofline": {"bound": "alu-issue", "kernel": "sf_dtw_score_kernel<8,false>",
                          "achieved": dtw_cells_per_s / 1e9, "peak": peak_cells / 1e9, "unit": "GCUPS",
                          "frac": dtw_cells_per_s / peak_cells,
-                         "traffic": NCU_DTW_TRAFFIC["bytes"] if len(sigs) == NCU_DTW_TRAFFIC["reads"] else None,
-                         "traffic_note": "bytes per launch, ncu capture of this workload (profiles/r01_ncu_summary.md); "
+                         "traffic": NCU_DTW_TRAFFIC["bytes"] * len(sigs) / NCU_DTW_TRAFFIC["reads"],
+                         "traffic_note": "bytes per launch, scaled by reads from the ncu capture of this workload at 5920 reads "
+                                         "(profiles/r01_ncu_summary.md); "
                                          "algorithmic HBM bytes are 0.016 B/cell (8 MB reference stream, L2 resident) "
                                          "plus the wavefront checkpoints (0.66 MB/read)",
                          "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
