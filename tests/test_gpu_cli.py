@@ -157,3 +157,45 @@ def test_cli_c4_scale_matches_reference_binary(cli, tmp_path):
     assert want.count("\n") == 16
     assert "".join(r.stdout.splitlines(keepends=True)[:16]) == want
     assert r.stdout.count("\n") == 600
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_cli_fuzz_matches_oracle_paf_and_sam(cli, tmp_path, seed):
+    """seeded fuzz of the command line (C host + GPU) against the CPU oracle: random chemistry, flags, q, p
+    (incl. -1), contigs and reads; PAF and SAM text must be identical"""
+    rng = np.random.default_rng(8000 + seed)
+    rna = bool(rng.integers(0, 2))
+    k = 5 if rna else int(rng.choice([6, 9]))
+    flags = 0
+    p = int(rng.choice([0, 10, 50, 50, 120]))
+    if rna:
+        flags = H.F_RNA | int(rng.choice([0, H.F_DTW, H.F_INV, H.F_REF, H.F_DTW | H.F_REF, H.F_INV | H.F_REF]))
+        if rng.integers(0, 3) == 0 and not (flags & H.F_INV):
+            p = -1
+    if p >= 0 and rng.integers(0, 3) == 0:
+        flags |= H.F_END
+    q = int(rng.choice([25, 60, 97, 130, 250, 250, 333]))
+    mean, stdv = synth.make_model(k, seed=41 + seed)
+    seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(700, 4000, size=int(rng.integers(1, 5)))]
+    names = [f"c{i}" for i in range(len(seqs))]
+    sigs, scs = [], []
+    for r in range(7):
+        if rna and p < 0 and r % 2 == 0:
+            s, _ = synth.simulate_rna_reads_with_tail(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), bases_per_read=500)
+        else:
+            s, _ = synth.simulate_reads(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), rna=rna,
+                                        bases_per_read=int(rng.choice([150, 300, 450, 700])), min_samples=700)
+        sigs.append(s[0])
+        scs.append(synth.RNA_SCALING if rna else synth.DNA_SCALING)
+    ids = [f"r{i}" for i in range(len(sigs))]
+    fa, s5, mf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.blow5"), str(tmp_path / "model.txt")
+    synth.write_fasta(fa, names, seqs)
+    synth.write_blow5(s5, ids, sigs, rna=rna, kit="sqk-lsk114" if k == 9 else None, scalings=scs)
+    synth.write_model_file(mf, k, mean, stdv)
+    c = dict(q=q, p=p, flags=flags)
+    out, _ = _run(cli, c, fa, s5, mf, ["-K", "3"])
+    assert out == H.oracle_paf(names, seqs, mean, k, ids, sigs, scs, flags, q, p), (flags, q, p)
+    if not flags & H.F_DTW:
+        out, _ = _run(cli, c, fa, s5, mf, ["--sam"])
+        out = "".join(l for l in out.splitlines(keepends=True) if not l.startswith("@PG"))
+        assert out == H.oracle_sam(names, seqs, mean, k, ids, sigs, scs, flags, q, p), (flags, q, p)

@@ -161,3 +161,48 @@ def test_oracle_sam_matches_reference_golden(case):
     want = open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()
     want = "".join(l for l in want.splitlines(keepends=True) if not l.startswith("@PG"))
     assert got == want
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("seed", range(16))
+def test_oracle_fuzz_against_reference_binary(tmp_path, seed):
+    """seeded fuzz of the whole path, oracle vs the unmodified reference binary run right now (build container
+    only): chemistry, every flag combination the CLI accepts, q, p (incl. -1), contig counts / lengths, PAF and SAM"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7000 + seed)
+    rna = bool(rng.integers(0, 2))
+    k = 5 if rna else int(rng.choice([6, 9]))
+    flags = 0
+    p = int(rng.choice([0, 10, 50, 50, 120]))
+    if rna:
+        flags = H.F_RNA | int(rng.choice([0, H.F_DTW, H.F_INV, H.F_REF, H.F_DTW | H.F_REF, H.F_INV | H.F_REF]))
+        if rng.integers(0, 3) == 0 and not (flags & H.F_INV):
+            p = -1
+    if p >= 0 and rng.integers(0, 3) == 0:
+        flags |= H.F_END
+    q = int(rng.choice([25, 60, 97, 130, 250, 250, 333]))
+    mean, stdv = synth.make_model(k, seed=31 + seed)
+    seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(700, 4000, size=int(rng.integers(1, 5)))]
+    names = [f"c{i}" for i in range(len(seqs))]
+    sigs, scs = [], []
+    for r in range(6):
+        if rna and p < 0 and r % 2 == 0:
+            s, _ = synth.simulate_rna_reads_with_tail(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), bases_per_read=500)
+        else:
+            s, _ = synth.simulate_reads(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), rna=rna,
+                                        bases_per_read=int(rng.choice([150, 300, 450, 700])), min_samples=700)
+        sigs.append(s[0])
+        scs.append(synth.RNA_SCALING if rna else synth.DNA_SCALING)
+    ids = [f"r{i}" for i in range(len(sigs))]
+    fa, s5, mf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.blow5"), str(tmp_path / "model.txt")
+    synth.write_fasta(fa, names, seqs)
+    synth.write_blow5(s5, ids, sigs, rna=rna, kit="sqk-lsk114" if k == 9 else None, scalings=scs)
+    synth.write_model_file(mf, k, mean, stdv)
+    want = H.run_ref(fa, s5, mf, flags=flags, q=q, p=p)
+    got = H.oracle_paf(names, seqs, mean, k, ids, sigs, scs, flags, q, p)
+    assert got == want, (flags, q, p)
+    if not flags & H.F_DTW:  # the reference aborts on --dtw-std --sam (sigfish.c:669)
+        want = H.run_ref(fa, s5, mf, flags=flags, q=q, p=p, extra=["--sam"])
+        want = "".join(l for l in want.splitlines(keepends=True) if not l.startswith("@PG"))
+        assert H.oracle_sam(names, seqs, mean, k, ids, sigs, scs, flags, q, p) == want, (flags, q, p)
