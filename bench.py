@@ -226,7 +226,8 @@ def main():
         ctx.resubmit(0)
         ctx.collect(0)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per job, not per rank
+        sampler.start()
     barrier()
     tot = dtw = evt = trc = 0.0
     cells = 0.0
@@ -246,7 +247,8 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     sampler.stop_flag = True
-    sampler.join()
+    if rank == 0:
+        sampler.join()
     last = ctx.collect(0)
     assert last.tobytes() == first.tobytes(), "results changed between steps"
     mapped = int((last["qlen"] > 0).sum())
