@@ -35,7 +35,7 @@ struct sf_group {
     int64_t end;        // one past the last real column of the last segment
     int32_t seg0;       // first segment
     int32_t nseg;       // number of segments
-    int32_t ck_every;   // checkpoint period in 32-step blocks (0: none)
+    int32_t ck_every;   // checkpoint period in blocks of 32 macro-steps = 64 columns (0: none)
     int32_t n_ck;       // checkpoints per task in this group
     int64_t ck_prefix;  // checkpoints of earlier groups (per read)
 };
@@ -59,7 +59,7 @@ struct sf_readinfo {
     uint64_t start_raw, end_raw;
 };
 
-// final per-read hit (device -> host), 48 bytes
+// final per-read hit (device -> host), 32 bytes
 struct sf_hit {
     float score, score2;
     int32_t rid, strand;
