@@ -34,10 +34,13 @@ def run(name, ctx, sigs, sc, reps=3):
 
 
 def main():
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if a in ("c2", "c4", "c5")] or ["c2", "c4", "c5"]
     n_reads = 4096
     if "--reads" in sys.argv:
         n_reads = int(sys.argv[sys.argv.index("--reads") + 1])
+    q = 250
+    if "-q" in sys.argv:
+        q = int(sys.argv[sys.argv.index("-q") + 1])
     rng = np.random.default_rng(3)
     if "c2" in which:  # R9 DNA vs a 30 kb genome, both strands
         k = 6
@@ -62,10 +65,10 @@ def main():
         lm, _ = synth.make_model(k)
         n_tx = 5000
         seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(400, 4000, size=n_tx)]
-        sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=420)
+        sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=max(420, q + 170))
         for flags, nm in ((capi.SFGPU_RNA | capi.SFGPU_INV, "C5 5k transcripts inv"), (capi.SFGPU_RNA, "C5 5k transcripts"),
                           (capi.SFGPU_RNA | capi.SFGPU_DTW, "C5 5k transcripts dtw-std")):
-            ctx = capi.Context(lm, k, flags=flags, pore=2)
+            ctx = capi.Context(lm, k, flags=flags, pore=2, query_size=q)
             ctx.set_ref(seqs)
             run(nm, ctx, sigs, [synth.RNA_SCALING] * len(sigs))
             ctx.close()
