@@ -60,7 +60,7 @@ __host__ __device__ inline int sf_ckpt_floats(int R) { return (R + 2) * 32; }
 // queries of the default -q values (250, 500, 100) and q = multiples of R
 __host__ __device__ constexpr int sf_fast_rq(int R) { return R == 8 ? 1 : (R == 16 ? 3 : (R == 4 ? 3 : R - 1)); }
 
-__host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 7 : (R <= 16 ? 5 : (R <= 24 ? 4 : 3))); }
+__host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 7 : (R <= 16 ? 7 : (R <= 24 ? 4 : 3))); }
 
 // Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses whose base is made
 // opaque once per block: otherwise the compiler re-derives the ring / buffer address from its parts on

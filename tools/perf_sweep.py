@@ -65,7 +65,7 @@ def main():
         lm, _ = synth.make_model(k)
         n_tx = 5000
         seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(400, 4000, size=n_tx)]
-        sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=max(420, q + 170))
+        sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=max(420, q + 450))
         for flags, nm in ((capi.SFGPU_RNA | capi.SFGPU_INV, "C5 5k transcripts inv"), (capi.SFGPU_RNA, "C5 5k transcripts"),
                           (capi.SFGPU_RNA | capi.SFGPU_DTW, "C5 5k transcripts dtw-std")):
             ctx = capi.Context(lm, k, flags=flags, pore=2, query_size=q)
