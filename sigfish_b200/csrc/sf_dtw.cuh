@@ -60,6 +60,20 @@ __host__ __device__ inline int sf_ckpt_floats(int R) { return (R + 2) * 32; }
 // queries of the default -q values (250, 500, 100) and q = multiples of R
 __host__ __device__ constexpr int sf_fast_rq(int R) { return R == 8 ? 1 : (R == 16 ? 3 : (R == 4 ? 3 : R - 1)); }
 
+// Macro-steps unrolled together in the hot loop (body = U x (6R + 6) instructions x 16 bytes).  A fully unrolled
+// block fits the 32 KB L1.5 instruction cache up to R = 8 (27 KB: measured equal to partial unrolling); beyond
+// that the warps stall on instruction fetch (R = 16, 52 KB: no_instruction 5.5 stalled warps per issue, 6.9 TCUPS
+// against 8.1 with an 6.5 KB body), so larger tiles unroll only as many macro-steps as fit 8 KB.
+__host__ __device__ constexpr int sf_dtw_unroll(int R)
+{
+    if (32 * (6 * R + 6) * 16 <= 28 * 1024)
+        return 32;
+    int u = 16;
+    while (u > 1 && u * (6 * R + 6) * 16 > 8 * 1024)
+        u /= 2;
+    return u;
+}
+
 __host__ __device__ constexpr int sf_dtw_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? 7 : (R <= 16 ? 7 : (R <= 24 ? 4 : 3))); }
 
 // Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses whose base is made
@@ -105,11 +119,15 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
                                              const int lane, const int nz)
 {
     const unsigned full = 0xffffffffu;
-    const unsigned yb_s = sf_smem_addr(yb);
-    const unsigned last_s = sf_smem_addr(last);
+    // the 32 macro-steps are unrolled U at a time (see sf_dtw_unroll)
+    constexpr int U = sf_dtw_unroll(R);
+    unsigned yb_o = sf_smem_addr(yb);
+    unsigned last_o = sf_smem_addr(last);
+#pragma unroll 1
+    for (int s0 = 0; s0 < 32; s0 += U) {
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const float2 yy = sf_lds2(yb_s + 8 * s);
+    for (int s = 0; s < U; s++) {
+        const float2 yy = sf_lds2(yb_o + 8 * s);
         float upA = __shfl_up_sync(full, botA, 1);
         float upB = __shfl_up_sync(full, botB, 1);
         if (STD) {
@@ -147,19 +165,22 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
         botB = upB;
         if (is_lq) {
             if (RQ >= 0) {
-                sf_sts2(last_s + 8 * s, keepA, keepB);
+                sf_sts2(last_o + 8 * s, keepA, keepB);
             } else {
                 if (R % 2 == 0) { // 16-byte stores need (s*R + r) even
 #pragma unroll
                     for (int r = 0; r < R; r += 2)
-                        sf_sts4(last_s + 8 * (s * R + r), allA[r], L[r], allA[r + 1], L[r + 1]);
+                        sf_sts4(last_o + 8 * (s * R + r), allA[r], L[r], allA[r + 1], L[r + 1]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; r++)
-                        sf_sts2(last_s + 8 * (s * R + r), allA[r], L[r]);
+                        sf_sts2(last_o + 8 * (s * R + r), allA[r], L[r]);
                 }
             }
         }
+    }
+        yb_o += 8 * U;
+        last_o += 8 * U * (RQ >= 0 ? 1 : R);
     }
 }
 
