@@ -41,13 +41,15 @@ KMER = 9
 Q, P = 250, 50
 WORKLOAD = "C4: synthetic R10 DNA (k=9), reads x q=250 vs one 1 Mb contig, both strands"
 
-# The DTW inner loop issues 54 SASS instructions per warp for one macro-step of 32 lanes x R=8 rows x 2 columns
-# (cuobjdump of sf_dtw_score_kernel<8,false>: 32 FADD + 16 FMNMX3 + LDS.64 + 2 SHFL + 2 IMAD + STS.64), i.e. 27 per
-# column of 256 cells.  FMNMX3 runs on the half-rate ALU pipe and blocks the issue port for 2 cycles (measured:
-# tools/ubench_alu.cu, profiles/r01_ubench_alu.txt), so a column costs 27 + 8 = 35 issue slots.  DESIGN.md 5.1.
-SASS_PER_STEP = 27.0
-ISSUE_SLOTS_PER_STEP = 35.0
-ROWS_PER_LANE = 8
+# q = 250 reads run two per warp (sf_dtw_pair_kernel<16,false,9>: 16 lanes x R=16 rows each).  Its inner loop issues
+# 104 SASS instructions per warp for one macro-step of 32 lanes x 16 rows x 2 columns (cuobjdump: 64 FADD + 32 FMNMX3 +
+# LDS.64 + 2 SHFL + 2 IMAD + STS.64 + loop), i.e. 52 per column of 512 cells.  FMNMX3 runs on the half-rate ALU pipe
+# and blocks the issue port for 2 cycles (measured: tools/ubench_alu.cu, profiles/r01_ubench_alu.txt), so a column
+# costs 52 + 16 = 68 issue slots.  The floor of the recurrence itself is 2 FADD + 1 FMNMX3 = 4 slots per cell
+# (64 per column).  DESIGN.md 5.1.
+SASS_PER_STEP = 52.0
+ISSUE_SLOTS_PER_STEP = 68.0
+ROWS_PER_LANE = 16
 # DRAM traffic of one DTW launch from the committed `ncu --set full` capture (profiles/r01_ncu_summary.md:
 # dram__bytes_read.sum + dram__bytes_write.sum at 5920 reads); almost all of it is wavefront checkpoints
 NCU_DTW_TRAFFIC = {"reads": 5920, "bytes": 151.729408e6 + 3778.607e6}
@@ -299,7 +301,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "reads_per_s": job_reads / (e2e_ms * 1e-3)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "alu-issue", "kernel": "sf_dtw_score_kernel<8,false>",
+            "roofline": {"bound": "alu-issue", "kernel": "sf_dtw_pair_kernel<16,false,9>",
                          "achieved": dtw_cells_per_s / 1e9, "peak": peak_cells / 1e9, "unit": "GCUPS",
                          "frac": dtw_cells_per_s / peak_cells,
                          "traffic": NCU_DTW_TRAFFIC["bytes"] * len(sigs) / NCU_DTW_TRAFFIC["reads"],
@@ -309,7 +311,8 @@ def main():
                                          "plus the wavefront checkpoints (0.66 MB/read)",
                          "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
                                         f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
-                                        f"({SASS_PER_STEP:.0f} SASS per column, the 8 half-rate FMNMX3 counted twice)",
+                                        f"({SASS_PER_STEP:.0f} SASS per column, the {ROWS_PER_LANE} half-rate FMNMX3 counted twice)",
+                         "frac_of_recurrence_floor": dtw_cells_per_s / (sm_count * 4 * clk * 32 / 4.0),
                          "frac_if_every_sass_were_one_slot": dtw_cells_per_s / peak_naive,
                          "events_kernel_GBps": (job_samples / world) * 2 / (evt_ms * 1e-3) / 1e9 if evt_ms > 0 else None,
                          "hbm_peak_GBps": peaks.get("hbm_gbs")},

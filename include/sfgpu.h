@@ -54,7 +54,7 @@ typedef struct {
     int32_t kmer_size;    /* core->kmer_size */
     int32_t n_slots;      /* batches in flight (double buffering); 0 -> 2 */
     int32_t pore;         /* opt.pore_flag: 0 r9, 1 r10, 2 rna004 (only selects the jnn parameters) */
-    int32_t reserved[5];  /* [0], [1]: test knobs (checkpoint spacing, restart window); keep 0 */
+    int32_t reserved[5];  /* test knobs, keep 0: [0] checkpoint spacing, [1] restart window, [3] 1 = no read pairing */
 } sfgpu_opt_t;
 
 /* per-read output of the device stages: what normalise_single() leaves in db->qstart/qend

@@ -99,13 +99,14 @@ class Context:
 
     def __init__(self, level_mean: np.ndarray, kmer_size: int, flags: int = 0, query_size: int = 250,
                  prefix_size: int = 50, device: int = 0, n_slots: int = 2, ck_min_cols: int = 0,
-                 min_window: int = 0, pore: int = 0):
+                 min_window: int = 0, pore: int = 0, no_pairing: bool = False):
         L = lib()
         self._h = C.c_void_p()
         self.opt = Opt(device=device, flags=flags, query_size=query_size, prefix_size=prefix_size,
                        kmer_size=kmer_size, n_slots=n_slots, pore=pore)
         self.opt.reserved[0] = ck_min_cols  # test knob: checkpoint segments longer than this
         self.opt.reserved[1] = min_window   # test knob: restart distance of the start-coordinate pass
+        self.opt.reserved[3] = int(no_pairing)  # test knob: one read per warp even for q = 250 / 256
         lm = np.ascontiguousarray(level_mean, dtype=np.float32)
         assert lm.shape[0] == 4 ** kmer_size
         rc = L.sfgpu_create(C.byref(self._h), C.byref(self.opt), _ptr(lm))

@@ -47,7 +47,12 @@ struct sf_dtw_args {
     sf_taskres *res;        // [n_reads][n_groups]
     float *ckpt;            // [(read * ck_per_read + ck_prefix + k)][R+2][32]
     int64_t ck_per_read;
+    int32_t ck_floats;      // floats per checkpoint (max over the layouts in use)
     unsigned int *counter;
+    // optional indirection: the kernel works on reads list[0 .. *n_list) instead of 0 .. n_reads
+    const int32_t *list;
+    const int32_t *n_list;
+    int32_t q_full;         // pair kernel: every listed read has exactly this query length
 };
 
 // ring (float2 x 128) + last-row buffer (2 values per macro-step; 2R in the generic block)
@@ -113,10 +118,10 @@ __device__ __forceinline__ float sf_mask0(float v, int nz)
 // State between macro-steps: L[r] = row r at the lane's second column, botA/botB = bottom row at the
 // lane's two columns (read by the next lane one macro-step later), dprev = the `up` input of the second
 // column (the diagonal of row 0 at the next macro-step's first column).
-template <int R, bool STD, int RQ>
+template <int R, bool STD, int RQ, int W = 32>
 __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R], float &botA, float &botB,
                                              float &dprev, const float2 *yb, float *last, const bool is_lq,
-                                             const int lane, const int nz)
+                                             const int nz)
 {
     const unsigned full = 0xffffffffu;
     // the 32 macro-steps are unrolled U at a time (see sf_dtw_unroll)
@@ -128,10 +133,10 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
 #pragma unroll
     for (int s = 0; s < U; s++) {
         const float2 yy = sf_lds2(yb_o + 8 * s);
-        float upA = __shfl_up_sync(full, botA, 1);
-        float upB = __shfl_up_sync(full, botB, 1);
+        float upA = __shfl_up_sync(full, botA, 1, W);
+        float upB = __shfl_up_sync(full, botB, 1, W);
         if (STD) {
-            if (lane == 0) {
+            if (!nz) { // first lane of the read
                 upA = yy.x == SF_INF ? 0.0f : SF_INF;
                 upB = yy.y == SF_INF ? 0.0f : SF_INF;
             }
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
     float2 *ring = sf_smem2 + warp * (sf_smem_floats_per_warp(R) / 2);
     float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
-    const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)a.n_reads;
+    const int n_list = a.list ? *a.n_list : a.n_reads;
+    const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)n_list;
 
     for (;;) {
         unsigned task = 0;
@@ -202,8 +208,9 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
         task = __shfl_sync(full, task, 0);
         if (task >= n_tasks)
             break;
-        const int gi = task / (unsigned)a.n_reads;
-        const int read = task - gi * a.n_reads;
+        const int gi = task / (unsigned)n_list;
+        const int li = task - gi * n_list;
+        const int read = a.list ? a.list[li] : li;
         const int gid = a.order[gi];
         const sf_group grp = a.groups[gid];
         sf_taskres *out = a.res + (size_t)read * a.n_groups + gid;
@@ -271,9 +278,9 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
             const float2 *yb = ring + ((b & 1) ? 32 : 64) - lane;
 
             if (fast)
-                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, lane, nz);
+                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
             else
-                sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, lane, nz);
+                sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
             __syncwarp();
 
             // ---- last-row chunk minima (sigfish.c:891-901): this block produced the last row of columns
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 
             // ---- checkpoint of the skewed wavefront (for the start-coordinate pass) ----
             if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)sf_ckpt_floats(R);
+                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     c[r * 32 + lane] = L[r];
@@ -363,5 +370,208 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
         if (lane == 0) {
             out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
         }
+    }
+}
+
+
+// ---- two full-length reads per warp ---------------------------------------------------------------------
+// For q <= 256 a read needs only 16 lanes when each lane holds 16 rows, and the per-macro-step overheads (LDS,
+// shuffles, border IMADs, last-row store) are then shared by twice the cells (measured at R = 16: 8.1 TCUPS
+// against 7.7 at R = 8).  Lanes 0-15 carry read list[2u], lanes 16-31 read list[2u+1]; both stream the same
+// segment group, so the ring and all chunk bookkeeping are shared and only the minima are kept per read.  Every
+// listed read has exactly q_full events (sf_partition_kernel), i.e. the last query row is register RQ of lane
+// (q_full-1)/R of its half; shorter queries go through sf_dtw_score_kernel.  Checkpoints use the half-warp
+// layout [R+2][16] (consumed by sf_trace_read<R, STD, 16>).
+#define SF_PAIR_LANES 16
+// last-row staging of one read: 64 floats + 4 of padding, so that the two storing lanes hit different banks
+#define SF_PAIR_LAST 68
+__host__ __device__ inline int sf_pair_smem_floats_per_warp() { return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST; }
+
+template <int R, bool STD, int RQ>
+__global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_pair_kernel(const sf_dtw_args a)
+{
+    constexpr int W = SF_PAIR_LANES;
+    extern __shared__ float2 sf_smem2[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int ll = lane & (W - 1);  // lane inside the read
+    const int half = lane / W;      // which read of the pair
+    float2 *ring = sf_smem2 + warp * (sf_pair_smem_floats_per_warp() / 2);
+    float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
+    const unsigned full = 0xffffffffu;
+    const int n_list = *a.n_list;
+    const int n_units = (n_list + 1) / 2;
+    const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)n_units;
+    const int qlen = a.q_full;
+    const int lq = (qlen - 1) / R;  // lane (inside the half) holding the last query row; its register is RQ
+    const bool is_lq = ll == lq;
+    const int nz = ll != 0;
+
+    for (;;) {
+        unsigned task = 0;
+        if (lane == 0)
+            task = atomicAdd(a.counter, 1u);
+        task = __shfl_sync(full, task, 0);
+        if (task >= n_tasks)
+            break;
+        const int gi = task / (unsigned)n_units;
+        const int unit = task - gi * n_units;
+        const int gid = a.order[gi];
+        const sf_group grp = a.groups[gid];
+        const int idx = 2 * unit + half;
+        const bool valid = idx < n_list;           // an odd list: the second half repeats the first read
+        const int read = a.list[valid ? idx : 2 * unit];
+
+        float x[R], L[R];
+        const float *q = a.queries + (size_t)read * a.q_cap;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int row = ll * R + r;
+            x[r] = row < qlen ? q[row] : 0.0f;
+            L[r] = SF_INF;
+        }
+        float botA = SF_INF, botB = SF_INF;
+        float dprev = (ll == 0 && !STD) ? 0.0f : SF_INF;
+
+        const float *y = a.stream + grp.begin;
+        const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
+        const int n_blocks = ((n_pos - 1) / 2 + lq + 32) >> 5;
+
+        __syncwarp();
+        {
+            const int c0 = 2 * lane, c1 = c0 + 1;
+            const float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
+            ring[lane] = v; ring[64 + lane] = v;
+            const float2 inf2 = make_float2(SF_INF, SF_INF);
+            ring[32 + lane] = inf2; ring[96 + lane] = inf2;
+        }
+        __syncwarp();
+
+        // chunk bookkeeping: shared by the two reads (same query length, same segments)
+        int si = grp.seg0;
+        const int si_end = grp.seg0 + grp.nseg;
+        sf_seg seg = a.segs[si];
+        int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
+        int chunk = 0;
+        int clo = STD ? hi - 1 : lo;
+        int chi = STD ? hi : min(lo + qlen, hi);
+        // per read: the lanes of a half track the last row of their own read
+        float rmin = SF_INF, s1 = SF_INF, s2 = SF_INF;
+        int rpos = -1, bseg = -1, bchunk = 0, bpos = -1;
+        int ck = 0;
+
+        for (int b = 0; b < n_blocks; b++) {
+            const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
+            const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
+            const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
+            const float2 *yb = ring + ((b & 1) ? 32 : 64) - ll;
+
+            sf_dtw_block<R, STD, RQ, W>(x, L, botA, botB, dprev, yb, last + SF_PAIR_LAST * half, is_lq, nz);
+            __syncwarp();
+
+            // ---- last-row chunk minima: this block produced columns p0 .. p0+63 of both reads; lane ll of a
+            //      half looks at p0+4ll .. p0+4ll+3 of its own read ----
+            {
+                const int p0 = SF_BLOCK_COLS * b - 2 * lq;
+                const int pos0 = p0 + 4 * ll;
+                const float4 v = *reinterpret_cast<const float4 *>(last + SF_PAIR_LAST * half + 4 * ll);
+                for (;;) {
+                    if (pos0 >= clo && pos0 < chi && v.x < rmin) { rmin = v.x; rpos = pos0; }
+                    if (pos0 + 1 >= clo && pos0 + 1 < chi && v.y < rmin) { rmin = v.y; rpos = pos0 + 1; }
+                    if (pos0 + 2 >= clo && pos0 + 2 < chi && v.z < rmin) { rmin = v.z; rpos = pos0 + 2; }
+                    if (pos0 + 3 >= clo && pos0 + 3 < chi && v.w < rmin) { rmin = v.w; rpos = pos0 + 3; }
+                    if (chi > p0 + SF_BLOCK_COLS)
+                        break;
+                    float m = rmin;
+                    int mp = rpos;
+#pragma unroll
+                    for (int o = W / 2; o > 0; o >>= 1) { // stays inside the half
+                        const float om = __shfl_xor_sync(full, m, o);
+                        const int op = __shfl_xor_sync(full, mp, o);
+                        if (om < m || (om == m && (unsigned)op < (unsigned)mp)) {
+                            m = om;
+                            mp = op;
+                        }
+                    }
+                    if (m <= s1) {
+                        s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
+                    } else if (m < s2) {
+                        s2 = m;
+                    }
+                    rmin = SF_INF;
+                    rpos = -1;
+                    clo = chi;
+                    chunk++;
+                    if (clo >= hi) {
+                        si++;
+                        chunk = 0;
+                        if (si < si_end) {
+                            seg = a.segs[si];
+                            lo = (int)(seg.off - grp.begin);
+                            hi = lo + seg.rlen;
+                            clo = STD ? hi - 1 : lo;
+                        } else {
+                            clo = 0x7fffffff;
+                            hi = 0x7fffffff;
+                        }
+                    }
+                    chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
+                }
+            }
+
+            // ---- checkpoint (half-warp layout), one per read ----
+            if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
+                if (valid) {
+                    float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        c[r * W + ll] = L[r];
+                    c[R * W + ll] = dprev;
+                    c[(R + 1) * W + ll] = botA;
+                }
+                ck++;
+            }
+
+            {
+                const int slot = ((b + 1) & 1) * 32 + lane;
+                const float2 v = make_float2(yn0, yn1);
+                ring[slot] = v;
+                ring[slot + 64] = v;
+            }
+            __syncwarp();
+        }
+
+        if (ll == 0 && valid) {
+            sf_taskres *out = a.res + (size_t)read * a.n_groups + gid;
+            out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
+        }
+    }
+}
+
+// Splits the reads of a batch into those with exactly q_full events (pair kernel; flagged with status bit 5)
+// and the rest (warp-per-read kernel), both in ascending read order.  One warp.
+__global__ void sf_partition_kernel(sf_readinfo *info, int n_reads, int q_full, int32_t *list_full, int32_t *list_other,
+                                    int32_t *counts)
+{
+    const int lane = threadIdx.x;
+    int nf = 0, no = 0;
+    for (int base = 0; base < n_reads; base += 32) {
+        const int i = base + lane;
+        const int ql = i < n_reads ? info[i].qlen : -1;
+        const bool isf = ql == q_full, iso = ql > 0 && !isf;
+        const unsigned mf = __ballot_sync(0xffffffffu, isf), mo = __ballot_sync(0xffffffffu, iso);
+        const unsigned below = (1u << lane) - 1u;
+        if (isf) {
+            list_full[nf + __popc(mf & below)] = i;
+            info[i].status |= 32;
+        }
+        if (iso)
+            list_other[no + __popc(mo & below)] = i;
+        nf += __popc(mf);
+        no += __popc(mo);
+    }
+    if (lane == 0) {
+        counts[0] = nf;
+        counts[1] = no;
     }
 }

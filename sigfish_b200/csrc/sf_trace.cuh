@@ -34,6 +34,7 @@ struct sf_trace_args {
     const sf_taskres *res;
     const float *ckpt;
     int64_t ck_per_read;
+    int32_t ck_floats;        // floats per checkpoint
     sf_hit *hits;
     int32_t min_window;       // restart at least this many columns before the target
 };
@@ -64,60 +65,18 @@ __device__ __forceinline__ void sf_top_merge(sf_top &a, const sf_top &b)
     }
 }
 
-template <int R, bool STD>
-__global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
+// Start coordinate of the winning cell (qlen-1, top_pos of segment `seg`) for one read; W lanes hold the read
+// (32: one read per warp; 16: the half-warp layout of sf_dtw_pair_kernel, whose checkpoints are [R+2][16]).
+// With W = 16 the upper half of the warp mirrors the lower half.
+template <int R, bool STD, int W>
+__device__ __forceinline__ int sf_trace_start(const sf_trace_args &a, const int read, const int lane_in_warp, const int qlen,
+                                              const int top_pos, const sf_seg &seg, const sf_group &grp)
 {
-    const int lane = threadIdx.x & 31;
-    const int read = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned full = 0xffffffffu;
-    if (read >= a.n_reads)
-        return;
-    const int qlen = a.info[read].qlen;
-    sf_hit hit;
-    hit.score = SF_INF; hit.score2 = SF_INF; hit.rid = -1; hit.strand = 0;
-    hit.pos_st = -1; hit.pos_end = -1; hit.seg = -1; hit.pad = 0;
-    if (qlen <= 0) {
-        if (lane == 0) a.hits[read] = hit;
-        return;
-    }
-
-    // ---- merge the per-group results of this read ----
-    sf_top top;
-    top.s1 = SF_INF; top.s2 = SF_INF; top.seg = -1; top.chunk = 0; top.pos = -1;
-    for (int g = lane; g < a.n_groups; g += 32) {
-        const sf_taskres tr = a.res[(size_t)read * a.n_groups + g];
-        sf_top b; b.s1 = tr.s1; b.s2 = tr.s2; b.seg = tr.seg; b.chunk = tr.chunk; b.pos = tr.pos;
-        sf_top_merge(top, b);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sf_top b;
-        b.s1 = __shfl_xor_sync(full, top.s1, o);
-        b.s2 = __shfl_xor_sync(full, top.s2, o);
-        b.seg = __shfl_xor_sync(full, top.seg, o);
-        b.chunk = __shfl_xor_sync(full, top.chunk, o);
-        b.pos = __shfl_xor_sync(full, top.pos, o);
-        sf_top_merge(top, b);
-    }
-    hit.score = top.s1; hit.score2 = top.s2; hit.seg = top.seg;
-    if (top.seg < 0 || top.pos < 0) {
-        if (top.seg >= 0) {
-            const sf_seg sg = a.segs[top.seg];
-            hit.rid = sg.rid; hit.strand = sg.strand; hit.pos_end = top.pos;
-        }
-        if (lane == 0) a.hits[read] = hit;
-        return;
-    }
-    const sf_seg seg = a.segs[top.seg];
-    hit.rid = seg.rid; hit.strand = seg.strand; hit.pos_end = top.pos;
-
-    // ---- start-coordinate pass ----
-    const int gid = a.seg_group[top.seg];
-    const sf_group grp = a.groups[gid];
+    const int lane = lane_in_warp & (W - 1);
     const float *y = a.stream + grp.begin;          // position 0 = the group's leading sentinel
     const int n_pos = (int)(grp.end - grp.begin);
     const int seg_lo = (int)(seg.off - grp.begin);  // position of the segment's column 0
-
     float x[R];
     const float *q = a.queries + (size_t)read * a.q_cap;
 #pragma unroll
@@ -127,7 +86,7 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
     }
 
     int trow = qlen - 1;            // target cell
-    int tpos = seg_lo + top.pos;
+    int tpos = seg_lo + top_pos;
     int result = -1;
     int ck_limit = grp.n_ck;        // only checkpoints below this index may be used
 
@@ -162,15 +121,15 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
             // (bottom row only: botA), off 2 = the previous pair's second column (bottom row only: the next
             // lane's dprev).
             T = 32 * (k + 1) * grp.ck_every - 1;
-            const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + k) * (size_t)sf_ckpt_floats(R);
+            const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + k) * (size_t)a.ck_floats;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                L[r] = c[r * 32 + lane];
+                L[r] = c[r * W + lane];
                 S[r] = -1 - 4 * (lane * R + r);
             }
-            dprev = c[R * 32 + lane];
+            dprev = c[R * W + lane];
             sdprev = -1 - (4 * (lane * R - 1) + 2);
-            botA = c[(R + 1) * 32 + lane];
+            botA = c[(R + 1) * W + lane];
             sbotA = -1 - (4 * (lane * R + R - 1) + 1);
             T0 = T + 1;
         } else {
@@ -191,14 +150,14 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
         // reference events: 32 pairs at a time, handed to the lanes by shuffle
         float yp0, yp1;
         {
-            const long long c0 = 2ll * (T0 - 32 + lane);
+            const long long c0 = 2ll * (T0 - 32 + lane_in_warp);
             yp0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
             yp1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
         }
         const int n_blk = (T_end - T0) / 32 + 1;
         for (int blk = 0; blk < n_blk; blk++) {
             const int Tb = T0 + 32 * blk;
-            const long long c0 = 2ll * (Tb + lane);
+            const long long c0 = 2ll * (Tb + lane_in_warp);
             const float yc0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
             const float yc1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
 #pragma unroll 2
@@ -210,10 +169,10 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
                 const float b0 = __shfl_sync(full, yp0, src), b1 = __shfl_sync(full, yp1, src);
                 const float yA = s32 >= lane ? a0 : b0;
                 const float yB = s32 >= lane ? a1 : b1;
-                float upA = __shfl_up_sync(full, botA, 1);
-                float upB = __shfl_up_sync(full, botB, 1);
-                int supA = __shfl_up_sync(full, sbotA, 1);
-                int supB = __shfl_up_sync(full, sbotB, 1);
+                float upA = __shfl_up_sync(full, botA, 1, W);
+                float upB = __shfl_up_sync(full, botB, 1, W);
+                int supA = __shfl_up_sync(full, sbotA, 1, W);
+                int supB = __shfl_up_sync(full, sbotB, 1, W);
                 if (lane == 0) {
                     upA = STD ? (yA == SF_INF ? 0.0f : SF_INF) : 0.0f;
                     upB = STD ? (yB == SF_INF ? 0.0f : SF_INF) : 0.0f;
@@ -266,6 +225,66 @@ __global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
         tpos = 2 * (T - trow / R) + 1 - (code & 3);
         ck_limit = k; // strictly earlier restart next time
     }
+    return result;
+}
+
+// R2 > 0: reads flagged with status bit 5 were aligned by sf_dtw_pair_kernel<R2> (half-warp checkpoints)
+template <int R, bool STD, int R2>
+__global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int read = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned full = 0xffffffffu;
+    if (read >= a.n_reads)
+        return;
+    const int qlen = a.info[read].qlen;
+    sf_hit hit;
+    hit.score = SF_INF; hit.score2 = SF_INF; hit.rid = -1; hit.strand = 0;
+    hit.pos_st = -1; hit.pos_end = -1; hit.seg = -1; hit.pad = 0;
+    if (qlen <= 0) {
+        if (lane == 0) a.hits[read] = hit;
+        return;
+    }
+
+    // ---- merge the per-group results of this read ----
+    sf_top top;
+    top.s1 = SF_INF; top.s2 = SF_INF; top.seg = -1; top.chunk = 0; top.pos = -1;
+    for (int g = lane; g < a.n_groups; g += 32) {
+        const sf_taskres tr = a.res[(size_t)read * a.n_groups + g];
+        sf_top b; b.s1 = tr.s1; b.s2 = tr.s2; b.seg = tr.seg; b.chunk = tr.chunk; b.pos = tr.pos;
+        sf_top_merge(top, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sf_top b;
+        b.s1 = __shfl_xor_sync(full, top.s1, o);
+        b.s2 = __shfl_xor_sync(full, top.s2, o);
+        b.seg = __shfl_xor_sync(full, top.seg, o);
+        b.chunk = __shfl_xor_sync(full, top.chunk, o);
+        b.pos = __shfl_xor_sync(full, top.pos, o);
+        sf_top_merge(top, b);
+    }
+    hit.score = top.s1; hit.score2 = top.s2; hit.seg = top.seg;
+    if (top.seg < 0 || top.pos < 0) {
+        if (top.seg >= 0) {
+            const sf_seg sg = a.segs[top.seg];
+            hit.rid = sg.rid; hit.strand = sg.strand; hit.pos_end = top.pos;
+        }
+        if (lane == 0) a.hits[read] = hit;
+        return;
+    }
+    const sf_seg seg = a.segs[top.seg];
+    hit.rid = seg.rid; hit.strand = seg.strand; hit.pos_end = top.pos;
+
+    // ---- start-coordinate pass ----
+    const int gid = a.seg_group[top.seg];
+    const sf_group grp = a.groups[gid];
+
+    int result;
+    if (R2 > 0 && (a.info[read].status & 32))
+        result = sf_trace_start<(R2 > 0 ? R2 : R), STD, 16>(a, read, lane, qlen, top.pos, seg, grp);
+    else
+        result = sf_trace_start<R, STD, 32>(a, read, lane, qlen, top.pos, seg, grp);
     hit.pos_st = result;
     if (lane == 0) a.hits[read] = hit;
 }

@@ -59,7 +59,8 @@ struct sf_slot {
     sf_taskres *d_res = nullptr;
     float *d_ckpt = nullptr;
     sf_hit *d_hits = nullptr;
-    unsigned int *d_counter = nullptr;
+    unsigned int *d_counter = nullptr;  // [2] task queues of the two DTW kernels
+    int32_t *d_list_full = nullptr, *d_list_other = nullptr, *d_counts = nullptr; // sf_partition_kernel
     // state
     int32_t n_reads = 0;
     int64_t n_samples = 0; // padded
@@ -73,6 +74,10 @@ struct sf_slot {
 struct sfgpu_ctx {
     sfgpu_opt_t opt;
     int R = 0, q_cap = 0, ev_cap = 0, ev_cap_a = 0;
+    // two full-length reads per warp (sf_dtw_pair_kernel): rows per lane and register of the last row; 0: off
+    int R2 = 0, RQ2 = 0;
+    int ck_floats = 0;          // floats per wavefront checkpoint (max over the layouts in use)
+    int pair_blocks_per_sm = 0;
     int sm_count = 0;
     float *d_level_mean = nullptr;
     // reference
@@ -145,6 +150,7 @@ void slot_free_buffers(sf_slot &s)
     dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
     dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
+    dfree(s.d_list_full); dfree(s.d_list_other);
     s.cap_reads = 0;
     s.cap_samples = 0;
 }
@@ -165,6 +171,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
         dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
+        dfree(s.d_list_full); dfree(s.d_list_other);
         s.cap_reads = 0;
         const size_t n = (size_t)cap;
         SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
@@ -180,9 +187,11 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         SF_CUDA(c, cudaMalloc(&s.d_info, sizeof(sf_readinfo) * n));
         SF_CUDA(c, cudaMalloc(&s.d_res, sizeof(sf_taskres) * n * std::max(1, c->n_groups)));
         if (c->ck_per_read > 0)
-            SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)sf_ckpt_floats(c->R)));
+            SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)c->ck_floats));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
         SF_CUDA(c, cudaMalloc(&s.d_polya, sizeof(int64_t) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_list_full, sizeof(int32_t) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_list_other, sizeof(int32_t) * n));
         if (c->opt.flags & SFGPU_SAM) {
             SF_CUDA(c, cudaMalloc(&s.d_win_start, sizeof(uint64_t) * n * c->q_cap));
             SF_CUDA(c, cudaMalloc(&s.d_win_len, sizeof(float) * n * c->q_cap));
@@ -208,6 +217,31 @@ cudaError_t launch_dtw(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
+template <int RQ, bool STD> int pair_occupancy(size_t smem)
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_pair_kernel<16, STD, RQ>, SF_DTW_THREADS, smem);
+    return nb;
+}
+
+template <int RQ, bool STD> cudaError_t launch_pair(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
+{
+    sf_dtw_pair_kernel<16, STD, RQ><<<grid, SF_DTW_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// the pair kernel is instantiated for the query sizes 250 (last row in register 9 of its lane) and 256 (15)
+#define SF_DISPATCH_PAIR(RQ_, STD_, EXPR)                                                         \
+    do {                                                                                          \
+        if ((RQ_) == 9) {                                                                         \
+            constexpr int RQ = 9;                                                                 \
+            if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } \
+        } else {                                                                                  \
+            constexpr int RQ = 15;                                                                \
+            if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } \
+        }                                                                                         \
+    } while (0)
+
 template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaStream_t st)
 {
     const int warps = 4;
@@ -216,11 +250,17 @@ template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaSt
     return cudaGetLastError();
 }
 
-template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cudaStream_t st)
+template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cudaStream_t st, bool pair)
 {
     const int warps = 4;
     const int grid = (a.n_reads + warps - 1) / warps;
-    sf_trace_kernel<R, STD><<<grid, warps * 32, 0, st>>>(a);
+    if constexpr (R == 8) { // pairing exists for q = 250 / 256 only, i.e. R = 8 in the warp-per-read layout
+        if (pair) {
+            sf_trace_kernel<R, STD, 16><<<grid, warps * 32, 0, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
+    sf_trace_kernel<R, STD, 0><<<grid, warps * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -305,7 +345,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
     }
     SF_CUDA(c, cudaEventRecord(s.ev[2], st));
     if (n > 0) {
-        SF_CUDA(c, cudaMemsetAsync(s.d_counter, 0, sizeof(unsigned int), st));
+        SF_CUDA(c, cudaMemsetAsync(s.d_counter, 0, sizeof(unsigned int) * 2, st));
         sf_dtw_args da;
         da.stream = c->d_stream;
         da.segs = c->d_segs;
@@ -319,12 +359,35 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         da.res = s.d_res;
         da.ckpt = s.d_ckpt;
         da.ck_per_read = c->ck_per_read;
+        da.ck_floats = c->ck_floats;
         da.counter = s.d_counter;
+        da.list = nullptr;
+        da.n_list = nullptr;
+        da.q_full = c->opt.query_size;
         const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(c->R);
         const long long n_tasks = (long long)n * c->n_groups;
         const long long want = (n_tasks + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * c->dtw_blocks_per_sm));
         cudaError_t e = cudaErrorInvalidValue;
+        if (c->R2 > 0) {
+            // full-length reads two per warp, the others one per warp
+            sf_partition_kernel<<<1, 32, 0, st>>>(s.d_info, n, c->opt.query_size, s.d_list_full, s.d_list_other, s.d_counts);
+            SF_CUDA(c, cudaGetLastError());
+            sf_dtw_args pa = da;
+            pa.list = s.d_list_full;
+            pa.n_list = s.d_counts;
+            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
+            const long long pwant = ((n_tasks + 1) / 2 + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
+            const int pgrid = (int)std::max<long long>(1, std::min<long long>(pwant, (long long)c->sm_count * c->pair_blocks_per_sm));
+            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(pa, pgrid, psmem, st)));
+            SF_CUDA(c, e);
+            da.list = s.d_list_other;
+            da.n_list = s.d_counts + 1;
+            da.counter = s.d_counter + 1;
+            s.timing.dtw_launches++;
+            s.timing.other_launches++;
+        }
+        e = cudaErrorInvalidValue;
         SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(da, grid, smem, st)));
         SF_CUDA(c, e);
         s.timing.dtw_launches++;
@@ -344,10 +407,11 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ta.res = s.d_res;
         ta.ckpt = s.d_ckpt;
         ta.ck_per_read = c->ck_per_read;
+        ta.ck_floats = c->ck_floats;
         ta.hits = s.d_hits;
         ta.min_window = c->min_window;
         cudaError_t e = cudaErrorInvalidValue;
-        SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st)));
+        SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st, c->R2 > 0)));
         SF_CUDA(c, e);
         s.timing.other_launches++;
     }
@@ -630,7 +694,8 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             SF_CUDA(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             for (auto &e : s.ev)
                 SF_CUDA(c, cudaEventCreate(&e));
-            SF_CUDA(c, cudaMalloc(&s.d_counter, sizeof(unsigned int)));
+            SF_CUDA(c, cudaMalloc(&s.d_counter, sizeof(unsigned int) * 2));
+            SF_CUDA(c, cudaMalloc(&s.d_counts, sizeof(int32_t) * 2));
             memset(&s.timing, 0, sizeof s.timing);
         }
         const bool std_dtw = (opt->flags & SFGPU_DTW) != 0;
@@ -640,6 +705,19 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         if (nb <= 0)
             return fail(c, SFGPU_ECUDA, "DTW kernel does not fit on the device (R=%d)", rows);
         c->dtw_blocks_per_sm = nb;
+        c->ck_floats = sf_ckpt_floats(rows);
+        // two full-length reads per warp for the query sizes the pair kernel is built for (reserved[3] = 1: off)
+        if ((opt->query_size == 250 || opt->query_size == 256) && opt->reserved[3] == 0) {
+            c->R2 = 16;
+            c->RQ2 = (opt->query_size - 1) % 16;
+            c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);
+            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
+            int pnb = 0;
+            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (pnb = pair_occupancy<RQ, STD>(psmem)));
+            if (pnb <= 0)
+                return fail(c, SFGPU_ECUDA, "pair DTW kernel does not fit on the device");
+            c->pair_blocks_per_sm = pnb;
+        }
         return SFGPU_OK;
     }();
     if (rc != SFGPU_OK) {
@@ -663,6 +741,7 @@ void sfgpu_destroy(sfgpu_ctx *c)
             cudaStreamSynchronize(s.stream);
         slot_free_buffers(s);
         dfree(s.d_counter);
+        dfree(s.d_counts);
         for (auto &e : s.ev)
             if (e)
                 cudaEventDestroy(e);
@@ -919,7 +998,7 @@ int sfgpu_collect(sfgpu_ctx *c, int32_t slot, sfgpu_result_t *out)
         o.qstart = ri.qstart;
         o.qend = ri.qend;
         o.qlen = ri.qlen;
-        o.status = ri.status;
+        o.status = ri.status & 31; // bit 5 is internal (read went through the pair kernel)
         o.start_raw = ri.start_raw;
         o.end_raw = ri.end_raw;
         o.score = h.score;
@@ -1166,8 +1245,9 @@ int32_t sfgpu_wave_reads(const sfgpu_ctx *c)
 {
     if (!c || !c->have_ref || c->n_groups <= 0)
         return 0;
-    const int64_t warps = (int64_t)c->sm_count * c->dtw_blocks_per_sm * SF_DTW_WARPS;
-    return (int32_t)std::max<int64_t>(1, warps / c->n_groups);
+    const int64_t reads = c->R2 > 0 ? (int64_t)c->sm_count * c->pair_blocks_per_sm * SF_DTW_WARPS * 2
+                                    : (int64_t)c->sm_count * c->dtw_blocks_per_sm * SF_DTW_WARPS;
+    return (int32_t)std::max<int64_t>(1, reads / c->n_groups);
 }
 
 } // extern "C"

@@ -41,6 +41,8 @@ def main():
     q = 250
     if "-q" in sys.argv:
         q = int(sys.argv[sys.argv.index("-q") + 1])
+    nopair = "--no-pair" in sys.argv
+    waves = int(sys.argv[sys.argv.index("--waves") + 1]) if "--waves" in sys.argv else 0
     rng = np.random.default_rng(3)
     if "c2" in which:  # R9 DNA vs a 30 kb genome, both strands
         k = 6
@@ -55,10 +57,12 @@ def main():
         k = 9
         lm, _ = synth.make_model(k)
         seq = synth.random_sequence(1_000_000, rng)
-        sigs, _ = synth.simulate_reads([seq], k, lm, n_reads, seed=6, bases_per_read=450)
-        ctx = capi.Context(lm, k)
+        ctx = capi.Context(lm, k, query_size=q, no_pairing=nopair)
         ctx.set_ref([seq])
-        run("C4 1Mb R10 DNA q250", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
+        if waves:
+            n_reads = waves * ctx.wave_reads
+        sigs, _ = synth.simulate_reads([seq], k, lm, n_reads, seed=6, bases_per_read=max(450, q + 200))
+        run(f"C4 1Mb R10 DNA q{q}{' nopair' if nopair else ''}", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
         ctx.close()
     if "c5" in which:  # RNA004-like: many transcripts, 375 columns each, --rna --invert
         k = 9
@@ -68,7 +72,7 @@ def main():
         sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=max(420, q + 450))
         for flags, nm in ((capi.SFGPU_RNA | capi.SFGPU_INV, "C5 5k transcripts inv"), (capi.SFGPU_RNA, "C5 5k transcripts"),
                           (capi.SFGPU_RNA | capi.SFGPU_DTW, "C5 5k transcripts dtw-std")):
-            ctx = capi.Context(lm, k, flags=flags, pore=2, query_size=q)
+            ctx = capi.Context(lm, k, flags=flags, pore=2, query_size=q, no_pairing=nopair)
             ctx.set_ref(seqs)
             run(nm, ctx, sigs, [synth.RNA_SCALING] * len(sigs))
             ctx.close()
