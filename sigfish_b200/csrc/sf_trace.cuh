@@ -39,6 +39,18 @@ struct sf_trace_args {
     int32_t min_window;       // restart at least this many columns before the target
 };
 
+// a == b ? x : y as one FSETP + SEL (the compiler otherwise turns the backtrack rule's nested selection into a
+// branch per row)
+__device__ __forceinline__ int sf_sel_eq(float a, float b, int x, int y)
+{
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\tselp.s32 %0, %3, %4, p;\n\t}" : "=r"(r) : "f"(a), "f"(b), "r"(x), "r"(y));
+    return r;
+}
+
+struct sf_true { static constexpr bool value = true; };
+struct sf_false { static constexpr bool value = false; };
+
 struct sf_top {
     float s1, s2;
     int seg, chunk, pos;
@@ -154,63 +166,73 @@ __device__ __forceinline__ int sf_trace_start(const sf_trace_args &a, const int 
             yp0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
             yp1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
         }
+        // one macro-step; CAP: also pick up the start pointers of row tr (only the step that produces the target)
+        auto step = [&](const int s32, const int Tb, const float yc0, const float yc1, auto cap_tag) {
+            constexpr bool CAP = decltype(cap_tag)::value;
+            const int Tm = Tb + s32;
+            const int colA = 2 * (Tm - lane);
+            const int src = (s32 - lane) & 31;
+            const float a0 = __shfl_sync(full, yc0, src), a1 = __shfl_sync(full, yc1, src);
+            const float b0 = __shfl_sync(full, yp0, src), b1 = __shfl_sync(full, yp1, src);
+            const float yA = s32 >= lane ? a0 : b0;
+            const float yB = s32 >= lane ? a1 : b1;
+            float upA = __shfl_up_sync(full, botA, 1, W);
+            float upB = __shfl_up_sync(full, botB, 1, W);
+            int supA = __shfl_up_sync(full, sbotA, 1, W);
+            int supB = __shfl_up_sync(full, sbotB, 1, W);
+            if (lane == 0) {
+                upA = STD ? (yA == SF_INF ? 0.0f : SF_INF) : 0.0f;
+                upB = STD ? (yB == SF_INF ? 0.0f : SF_INF) : 0.0f;
+                supA = 0;
+                supB = 0;
+            }
+            const float next_dprev = upB;
+            const int next_sdprev = supB;
+            float dgA = dprev, dgB = upA;
+            int sdgA = sdprev, sdgB = supA;
+            int capA = 0, capB = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                // first column: left = L[r] (previous macro-step's second column)
+                const float mA = fminf(fminf(upA, dgA), L[r]);
+                int sA = sf_sel_eq(dgA, mA, sdgA, sf_sel_eq(L[r], mA, S[r], supA)); // diagonal, then left, then up
+                if (r == 0 && lane == 0)
+                    sA = colA - seg_lo; // start(0, j) = j
+                const float va = fabsf(x[r] - yA) + mA;
+                // second column: left = the value just computed
+                const float mB = fminf(fminf(upB, dgB), va);
+                int sB = sf_sel_eq(dgB, mB, sdgB, sf_sel_eq(va, mB, sA, supB));
+                if (r == 0 && lane == 0)
+                    sB = colA + 1 - seg_lo;
+                const float vb = fabsf(x[r] - yB) + mB;
+                dgA = L[r]; sdgA = S[r];
+                dgB = va; sdgB = sA;
+                L[r] = vb; S[r] = sB;
+                upA = va; supA = sA;
+                upB = vb; supB = sB;
+                if (CAP) {
+                    if (r == tr) { capA = sA; capB = sB; }
+                }
+            }
+            dprev = next_dprev; sdprev = next_sdprev;
+            botA = upA; sbotA = supA;
+            botB = upB; sbotB = supB;
+            if (CAP)
+                sres = tb ? capB : capA;
+        };
         const int n_blk = (T_end - T0) / 32 + 1;
         for (int blk = 0; blk < n_blk; blk++) {
             const int Tb = T0 + 32 * blk;
             const long long c0 = 2ll * (Tb + lane_in_warp);
             const float yc0 = (c0 >= 0 && c0 < n_pos) ? __ldg(y + c0) : SF_INF;
             const float yc1 = (c0 + 1 >= 0 && c0 + 1 < n_pos) ? __ldg(y + c0 + 1) : SF_INF;
+            // the last block stops at the macro-step that produces the target
+            const int n_plain = blk + 1 < n_blk ? 32 : T_end - Tb;
 #pragma unroll 2
-            for (int s32 = 0; s32 < 32; s32++) {
-                const int Tm = Tb + s32;
-                const int colA = 2 * (Tm - lane);
-                const int src = (s32 - lane) & 31;
-                const float a0 = __shfl_sync(full, yc0, src), a1 = __shfl_sync(full, yc1, src);
-                const float b0 = __shfl_sync(full, yp0, src), b1 = __shfl_sync(full, yp1, src);
-                const float yA = s32 >= lane ? a0 : b0;
-                const float yB = s32 >= lane ? a1 : b1;
-                float upA = __shfl_up_sync(full, botA, 1, W);
-                float upB = __shfl_up_sync(full, botB, 1, W);
-                int supA = __shfl_up_sync(full, sbotA, 1, W);
-                int supB = __shfl_up_sync(full, sbotB, 1, W);
-                if (lane == 0) {
-                    upA = STD ? (yA == SF_INF ? 0.0f : SF_INF) : 0.0f;
-                    upB = STD ? (yB == SF_INF ? 0.0f : SF_INF) : 0.0f;
-                    supA = 0;
-                    supB = 0;
-                }
-                const float next_dprev = upB;
-                const int next_sdprev = supB;
-                float dgA = dprev, dgB = upA;
-                int sdgA = sdprev, sdgB = supA;
-                int capA = 0, capB = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    // first column: left = L[r] (previous macro-step's second column)
-                    const float mA = fminf(fminf(upA, dgA), L[r]);
-                    int sA = (dgA == mA) ? sdgA : ((L[r] == mA) ? S[r] : supA);
-                    if (lane == 0 && r == 0)
-                        sA = colA - seg_lo; // start(0, j) = j
-                    const float va = fabsf(x[r] - yA) + mA;
-                    // second column: left = the value just computed
-                    const float mB = fminf(fminf(upB, dgB), va);
-                    int sB = (dgB == mB) ? sdgB : ((va == mB) ? sA : supB);
-                    if (lane == 0 && r == 0)
-                        sB = colA + 1 - seg_lo;
-                    const float vb = fabsf(x[r] - yB) + mB;
-                    dgA = L[r]; sdgA = S[r];
-                    dgB = va; sdgB = sA;
-                    L[r] = vb; S[r] = sB;
-                    upA = va; supA = sA;
-                    upB = vb; supB = sB;
-                    if (r == tr) { capA = sA; capB = sB; }
-                }
-                dprev = next_dprev; sdprev = next_sdprev;
-                botA = upA; sbotA = supA;
-                botB = upB; sbotB = supB;
-                if (Tm == T_end)
-                    sres = tb ? capB : capA;
-            }
+            for (int s32 = 0; s32 < n_plain; s32++)
+                step(s32, Tb, yc0, yc1, sf_false());
+            if (blk + 1 == n_blk)
+                step(n_plain, Tb, yc0, yc1, sf_true());
             yp0 = yc0;
             yp1 = yc1;
         }
@@ -228,9 +250,13 @@ __device__ __forceinline__ int sf_trace_start(const sf_trace_args &a, const int 
     return result;
 }
 
+// The pass is latency bound (one dependent chain of 2R+1 cells per macro-step), so resident warps matter more than
+// registers: up to 16 rows per lane the kernel is held to 128 registers (4 blocks of 4 warps per SM).
+__host__ __device__ constexpr int sf_trace_min_blocks(int R, int R2) { return (R > R2 ? R : R2) <= 16 ? 4 : 1; }
+
 // R2 > 0: reads flagged with status bit 5 were aligned by sf_dtw_pair_kernel<R2> (half-warp checkpoints)
 template <int R, bool STD, int R2>
-__global__ void __launch_bounds__(128) sf_trace_kernel(const sf_trace_args a)
+__global__ void __launch_bounds__(128, sf_trace_min_blocks(R, R2)) sf_trace_kernel(const sf_trace_args a)
 {
     const int lane = threadIdx.x & 31;
     const int read = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -504,6 +504,13 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
 
     // ---- groups: consecutive segments up to a column budget ----
     const int64_t budget = std::max<int64_t>(4096, std::min<int64_t>(65536, c->ref_columns / 64));
+    // checkpoint period: the long segments together get ~512 checkpoints per read (0.66 MB), whatever the
+    // genome size; never closer than ck_min_cols/4 (512) columns
+    int64_t long_cols = 0;
+    for (int s = 0; s < c->n_seg; s++)
+        if (c->segs[s].rlen > c->ck_min_cols)
+            long_cols += c->segs[s].rlen + 1;
+    const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, long_cols / 512);
     c->groups.clear();
     c->seg_group.assign(c->n_seg, 0);
     int s0 = 0;
@@ -527,8 +534,6 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
         if (g.end - g.begin > 0x7ffffff0ll)
             return fail(c, SFGPU_ELIMIT, "segment group too long");
         if (longest > c->ck_min_cols) {
-            // checkpoint period: ~1/256 of the segment, between ck_min_cols/4 (512) and 4096 columns
-            const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, std::min<int64_t>(4096, longest / 256));
             g.ck_every = (int32_t)((cols_per + SF_BLOCK_COLS - 1) / SF_BLOCK_COLS); // in blocks of 64 columns
             g.n_ck = (int32_t)(((g.end - g.begin) / SF_BLOCK_COLS) / g.ck_every);
         }

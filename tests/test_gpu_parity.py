@@ -681,3 +681,26 @@ def test_paired_and_unpaired_layouts_agree(q, std):
             assert bits(g["score"]) == bits(o.score) and bits(g["score2"]) == bits(o.score2), tag
             assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
     oref.close()
+
+
+def test_several_long_contigs_share_the_checkpoint_budget():
+    """the checkpoint period is set by the total length of the long segments (~512 checkpoints per read whatever
+    the genome size): six 40 kb contigs, both strands, production settings, every read against the oracle"""
+    k = 6
+    lm = model(k)
+    rng = np.random.default_rng(23)
+    seqs = [synth.random_sequence(40_000 + 1000 * i, rng) for i in range(6)]
+    sigs, truth = synth.simulate_reads(seqs, k, lm, 18, seed=9, bases_per_read=450)
+    sc = [synth.DNA_SCALING] * len(sigs)
+    ctx = capi.Context(lm, k)
+    ctx.set_ref(seqs)
+    got = ctx.map_batch(sigs, sc)
+    ref = H.OracleRef(seqs, lm, k, 0, 250)
+    hits = 0
+    for i, s in enumerate(sigs):
+        o = H.orc_map(ref, s, 8192.0, 10.0, 1402.882, 0, 250, 50)
+        assert_hit_equal(got[i], o, ("contigs", i), 0, 250, 50)
+        hits += int(got[i]["rid"] == truth[i][0])
+    assert hits >= 0.85 * len(sigs)
+    ref.close()
+    ctx.close()
