@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
     const unsigned full = 0xffffffffu;
     const int n_list = a.list ? *a.n_list : a.n_reads;
     const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)n_list;
+    // a kernel launched behind this one with programmatic stream serialisation (the pair kernel: it shares no data
+    // with this one) may start as soon as every block of this grid is resident
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     for (;;) {
         unsigned task = 0;

@@ -224,10 +224,20 @@ template <int RQ, bool STD> int pair_occupancy(size_t smem)
     return nb;
 }
 
+// launched behind sf_dtw_score_kernel in the same stream, allowed to start once that kernel's blocks are resident
 template <int RQ, bool STD> cudaError_t launch_pair(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
 {
-    sf_dtw_pair_kernel<16, STD, RQ><<<grid, SF_DTW_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SF_DTW_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sf_dtw_pair_kernel<16, STD, RQ>, a);
 }
 
 // the pair kernel is instantiated for the query sizes 250 (last row in register 9 of its lane) and 256 (15)
@@ -370,26 +380,34 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * c->dtw_blocks_per_sm));
         cudaError_t e = cudaErrorInvalidValue;
         if (c->R2 > 0) {
-            // full-length reads two per warp, the others one per warp
+            // Reads with exactly q events run two per warp (pair kernel), the others one per warp.  The two
+            // persistent kernels share the GPU: the warp-per-read kernel is launched first and releases its
+            // dependents as soon as its blocks are resident (griddepcontrol.launch_dependents); the pair kernel
+            // is launched with programmatic stream serialisation, so it starts then instead of after the end.
+            // Blocks of the first kernel that find the queue empty exit at once and leave their place to pair
+            // blocks: a few ragged reads in a batch cost no extra wave (a task on a 1 Mb contig runs ~0.2 s).
             sf_partition_kernel<<<1, 32, 0, st>>>(s.d_info, n, c->opt.query_size, s.d_list_full, s.d_list_other, s.d_counts);
             SF_CUDA(c, cudaGetLastError());
-            sf_dtw_args pa = da;
-            pa.list = s.d_list_full;
-            pa.n_list = s.d_counts;
+            s.timing.other_launches++;
+            sf_dtw_args oa = da;
+            oa.list = s.d_list_other;
+            oa.n_list = s.d_counts + 1;
+            oa.counter = s.d_counter + 1;
+            SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(oa, grid, smem, st)));
+            SF_CUDA(c, e);
+            s.timing.dtw_launches++;
+            da.list = s.d_list_full;
+            da.n_list = s.d_counts;
             const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
             const long long pwant = ((n_tasks + 1) / 2 + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
             const int pgrid = (int)std::max<long long>(1, std::min<long long>(pwant, (long long)c->sm_count * c->pair_blocks_per_sm));
-            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(pa, pgrid, psmem, st)));
+            e = cudaErrorInvalidValue;
+            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(da, pgrid, psmem, st)));
             SF_CUDA(c, e);
-            da.list = s.d_list_other;
-            da.n_list = s.d_counts + 1;
-            da.counter = s.d_counter + 1;
-            s.timing.dtw_launches++;
-            s.timing.other_launches++;
+        } else {
+            SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(da, grid, smem, st)));
+            SF_CUDA(c, e);
         }
-        e = cudaErrorInvalidValue;
-        SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(da, grid, smem, st)));
-        SF_CUDA(c, e);
         s.timing.dtw_launches++;
     }
     SF_CUDA(c, cudaEventRecord(s.ev[3], st));

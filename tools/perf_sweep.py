@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-stage device timings of the hot path on the workload shapes of BASELINE.json (development aid; the
-judged numbers come from bench.py).  Usage: python tools/perf_sweep.py [c2] [c4] [c5] [--reads N]"""
+judged numbers come from bench.py).  Usage: python tools/perf_sweep.py [c2] [c4] [c5] [--reads N] [--waves N] [-q Q] [--no-pair] [--ragged N]"""
 import os
 import sys
 import time
@@ -62,6 +62,9 @@ def main():
         if waves:
             n_reads = waves * ctx.wave_reads
         sigs, _ = synth.simulate_reads([seq], k, lm, n_reads, seed=6, bases_per_read=max(450, q + 200))
+        if "--ragged" in sys.argv:  # every N-th read cut short: fewer than p+q events, a ragged query
+            step = int(sys.argv[sys.argv.index("--ragged") + 1])
+            sigs = [s[:len(s) // 3] if i % step == 0 else s for i, s in enumerate(sigs)]
         run(f"C4 1Mb R10 DNA q{q}{' nopair' if nopair else ''}", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
         ctx.close()
     if "c5" in which:  # RNA004-like: many transcripts, 375 columns each, --rna --invert
