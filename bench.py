@@ -51,8 +51,8 @@ SASS_PER_STEP = 52.0
 ISSUE_SLOTS_PER_STEP = 68.0
 ROWS_PER_LANE = 16
 # DRAM traffic of one DTW launch from the committed `ncu --set full` capture (profiles/r01_ncu_summary.md:
-# dram__bytes_read.sum + dram__bytes_write.sum at 5920 reads); almost all of it is wavefront checkpoints
-NCU_DTW_TRAFFIC = {"reads": 5920, "bytes": 151.729408e6 + 3778.607e6}
+# dram__bytes_read.sum + dram__bytes_write.sum at 8288 reads); almost all of it is wavefront checkpoints
+NCU_DTW_TRAFFIC = {"reads": 8288, "bytes": 144.03328e6 + 4778.365e6}
 
 
 def make_workload(n_reads: int, seed: int, ref_len: int = REF_LEN):
@@ -305,10 +305,10 @@ def main():
                          "achieved": dtw_cells_per_s / 1e9, "peak": peak_cells / 1e9, "unit": "GCUPS",
                          "frac": dtw_cells_per_s / peak_cells,
                          "traffic": NCU_DTW_TRAFFIC["bytes"] * len(sigs) / NCU_DTW_TRAFFIC["reads"],
-                         "traffic_note": "bytes per launch, scaled by reads from the ncu capture of this workload at 5920 reads "
+                         "traffic_note": "bytes per launch, scaled by reads from the ncu capture of this workload at 8288 reads "
                                          "(profiles/r01_ncu_summary.md); "
                                          "algorithmic HBM bytes are 0.016 B/cell (8 MB reference stream, L2 resident) "
-                                         "plus the wavefront checkpoints (0.66 MB/read)",
+                                         "plus the wavefront checkpoints (0.59 MB/read)",
                          "peak_source": f"{sm_count} SMs x 4 schedulers x {clk / 1e6:.0f} MHz (median under load) / "
                                         f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
                                         f"({SASS_PER_STEP:.0f} SASS per column, the {ROWS_PER_LANE} half-rate FMNMX3 counted twice)",
