@@ -379,12 +379,13 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 
 // ---- two full-length reads per warp ---------------------------------------------------------------------
 // For q <= 256 a read needs only 16 lanes when each lane holds 16 rows, and the per-macro-step overheads (LDS,
-// shuffles, border IMADs, last-row store) are then shared by twice the cells (measured at R = 16: 8.1 TCUPS
+// shuffles, border IMADs, last-row store) are then shared by twice the cells (measured on a 1 Mb contig: 8.3 TCUPS
 // against 7.7 at R = 8).  Lanes 0-15 carry read list[2u], lanes 16-31 read list[2u+1]; both stream the same
 // segment group, so the ring and all chunk bookkeeping are shared and only the minima are kept per read.  Every
 // listed read has exactly q_full events (sf_partition_kernel), i.e. the last query row is register RQ of lane
-// (q_full-1)/R of its half; shorter queries go through sf_dtw_score_kernel.  Checkpoints use the half-warp
-// layout [R+2][16] (consumed by sf_trace_read<R, STD, 16>).
+// (q_full-1)/R of its half; shorter queries go through sf_dtw_score_kernel, which is launched first and releases
+// this kernel as soon as its blocks are resident (see run_stages in sfgpu.cu).  Checkpoints use the half-warp
+// layout [R+2][16] (consumed by sf_trace_start<R, STD, 16>).
 #define SF_PAIR_LANES 16
 // last-row staging of one read: 64 floats + 4 of padding, so that the two storing lanes hit different banks
 #define SF_PAIR_LAST 68
