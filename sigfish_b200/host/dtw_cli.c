@@ -3,7 +3,8 @@
  * Same options, defaults, validation rules and stderr summary as the reference's dtw_main()
  * (reference src/dtw_main.c:17-43 option table, 125-285 parsing + validation, 299-326 batch loop,
  * 331-345 summary).  Differences, all documented in INTEGRATION.md:
- *   - two batches are in flight: batch n+1 is loaded, decoded and submitted while batch n is on the GPUs;
+ *   - loading, record decoding and GPU submission run as pipeline stages on successive batches, with two
+ *     batches in flight on the devices;
  *   - without -K / -B the batch is sized to two full waves of DTW tasks per GPU instead of 512 reads / 20 MB;
  *   - --gpus N / --gpu-first I choose the devices (default: all visible B200s); reads are sharded
  *     over them with the reference replicated;
@@ -12,6 +13,7 @@
  */
 #include <errno.h>
 #include <getopt.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -96,6 +98,117 @@ static void print_help_msg(FILE *fp, const opt_t *opt)
     fprintf(fp, "   --full-ref                 map to the full reference\n");
     fprintf(fp, "   --from-end                 Map the end portion of the query instead of the beginning\n");
     fprintf(fp, "   --sam                      Output in SAM format\n");
+}
+
+/* ---- host pipeline: loader thread -> decoder thread -> main thread ---- */
+#define FEED_DBS 4
+
+typedef struct {
+    db_t *item[FEED_DBS + 1];
+    int head, count;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+} queue_t;
+
+static void queue_init(queue_t *q)
+{
+    memset(q, 0, sizeof *q);
+    pthread_mutex_init(&q->mu, NULL);
+    pthread_cond_init(&q->cv, NULL);
+}
+
+static void queue_push(queue_t *q, db_t *d)
+{
+    pthread_mutex_lock(&q->mu);
+    q->item[(q->head + q->count) % (FEED_DBS + 1)] = d;
+    q->count++;
+    pthread_cond_signal(&q->cv);
+    pthread_mutex_unlock(&q->mu);
+}
+
+/* oldest entry; NULL if the queue is empty and wait == 0 */
+static db_t *queue_pop(queue_t *q, int wait)
+{
+    db_t *d = NULL;
+    pthread_mutex_lock(&q->mu);
+    while (q->count == 0 && wait)
+        pthread_cond_wait(&q->cv, &q->mu);
+    if (q->count > 0) {
+        d = q->item[q->head];
+        q->head = (q->head + 1) % (FEED_DBS + 1);
+        q->count--;
+    }
+    pthread_mutex_unlock(&q->mu);
+    return d;
+}
+
+typedef struct {
+    core_t *core;
+    const opt_t *opt;
+    double realtime0;
+    db_t *db[FEED_DBS];
+    queue_t empty, loaded, parsed;
+    pthread_t loader, decoder;
+} feed_t;
+
+static void *feed_loader(void *p)
+{
+    feed_t *f = (feed_t *)p;
+    core_t *core = f->core;
+    int32_t n_loaded = 0;
+    for (;;) {
+        db_t *d = queue_pop(&f->empty, 1);
+        const ret_status_t st = load_db(core, d);
+        fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", "dtw_main", sf_realtime() - f->realtime0,
+                sf_cputime() / (sf_realtime() - f->realtime0), st.num_reads, st.num_bytes / (1000.0 * 1000.0));
+        /* src/dtw_main.c:299-300, 322-325 */
+        const int more = (st.num_reads >= core->opt.batch_size || st.num_bytes >= core->opt.batch_size_bytes) &&
+                         f->opt->debug_break != n_loaded;
+        n_loaded++;
+        d->last_batch = !more;
+        queue_push(&f->loaded, d);
+        if (!more)
+            return NULL;
+    }
+}
+
+static void *feed_decoder(void *p)
+{
+    feed_t *f = (feed_t *)p;
+    for (;;) {
+        db_t *d = queue_pop(&f->loaded, 1);
+        parse_db(f->core, d);
+        const int last = d->last_batch; /* read before the batch is handed on */
+        queue_push(&f->parsed, d);
+        if (last)
+            return NULL;
+    }
+}
+
+static void feed_init(feed_t *f, core_t *core, const opt_t *opt, double realtime0)
+{
+    memset(f, 0, sizeof *f);
+    f->core = core;
+    f->opt = opt;
+    f->realtime0 = realtime0;
+    queue_init(&f->empty);
+    queue_init(&f->loaded);
+    queue_init(&f->parsed);
+    for (int i = 0; i < FEED_DBS; i++) {
+        f->db[i] = init_db(core);
+        queue_push(&f->empty, f->db[i]);
+    }
+    if (pthread_create(&f->loader, NULL, feed_loader, f) || pthread_create(&f->decoder, NULL, feed_decoder, f)) {
+        SF_FATAL("%s", "pthread_create failed");
+    }
+}
+
+static void feed_destroy(feed_t *f)
+{
+    pthread_join(f->loader, NULL);
+    pthread_join(f->decoder, NULL);
+    for (int i = 0; i < FEED_DBS; i++)
+        free_db(f->db[i]);
 }
 
 int dtw_main(int argc, char *argv[])
@@ -231,44 +344,43 @@ int dtw_main(int argc, char *argv[])
         fprintf(stderr, "[%s] batch size: %d reads / %.1fM bytes on %d GPU(s)\n", __func__, core->opt.batch_size,
                 core->opt.batch_size_bytes / 1e6, core->num_gpus);
 
-    /* two batches in flight (one device slot each): while batch n runs, batch n+1 is loaded, decoded and
-     * submitted, so the tail of one batch overlaps the head of the next; output stays in input order */
-    db_t *db[2] = {init_db(core), init_db(core)};
-    ret_status_t st[2] = {{0, 0}, {0, 0}};
+    /* Three host stages run on different batches at once: a loader thread reads raw records, a decoder thread
+     * (fanning out to the -t workers) inflates them, and this thread packs / submits them to the GPUs and runs
+     * the epilogue.  Two batches are in flight on the devices (one slot each): the tail of one overlaps the
+     * head of the next.  Output stays in input order. */
+    feed_t feed;
+    feed_init(&feed, core, &opt, realtime0);
     if (core->opt.flag & SIGFISH_SAM)
         sam_hdr_wr(core->ref);
-    int more = 1, in_flight = 0, head = 0, next_db = 0;
-    int32_t n_loaded = 0;
-    while (more || in_flight) {
-        if (more && in_flight < 2) {
-            db_t *d = db[next_db];
-            st[next_db] = load_db(core, d);
-            fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) loaded\n", __func__, sf_realtime() - realtime0,
-                    sf_cputime() / (sf_realtime() - realtime0), st[next_db].num_reads, st[next_db].num_bytes / (1000.0 * 1000.0));
-            /* src/dtw_main.c:299-300, 322-325 */
-            more = (st[next_db].num_reads >= core->opt.batch_size || st[next_db].num_bytes >= core->opt.batch_size_bytes) &&
-                   opt.debug_break != n_loaded;
-            n_loaded++;
-            const double t0 = sf_realtime();
-            submit_db(core, d);
-            core->process_db_time += sf_realtime() - t0;
-            in_flight++;
-            next_db ^= 1;
-            continue;
+    db_t *flying[2] = {NULL, NULL};
+    int in_flight = 0, eof = 0;
+    while (!eof || in_flight) {
+        if (!eof && in_flight < 2) {
+            /* with a batch on the devices, only take the next one if it is ready: otherwise collect first */
+            db_t *d = queue_pop(&feed.parsed, in_flight == 0);
+            if (d) {
+                eof = d->last_batch;
+                const double t0 = sf_realtime();
+                submit_db(core, d);
+                core->process_db_time += sf_realtime() - t0;
+                flying[in_flight++] = d;
+                continue;
+            }
         }
-        db_t *d = db[head];
+        db_t *d = flying[0];
         const double t0 = sf_realtime();
         collect_db(core, d);
         core->process_db_time += sf_realtime() - t0;
         fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) processed\n", __func__, sf_realtime() - realtime0,
-                sf_cputime() / (sf_realtime() - realtime0), st[head].num_reads, st[head].num_bytes / (1000.0 * 1000.0));
+                sf_cputime() / (sf_realtime() - realtime0), d->n_rec, d->sum_bytes / (1000.0 * 1000.0));
         output_db(core, d);
         free_db_tmp(d);
-        head ^= 1;
+        flying[0] = flying[1];
+        flying[1] = NULL;
         in_flight--;
+        queue_push(&feed.empty, d);
     }
-    free_db(db[0]);
-    free_db(db[1]);
+    feed_destroy(&feed);
 
     fprintf(stderr, "[%s] total entries: %ld\tprefix fail: %ld\tignored: %ld\ttoo short: %ld", __func__,
             (long)core->total_reads, (long)core->prefix_fail, (long)core->ignored, (long)core->too_short);

@@ -361,8 +361,9 @@ static void *parse_worker(void *p)
     return NULL;
 }
 
-static void parse_db(core_t *core, db_t *db)
+void parse_db(core_t *core, db_t *db)
 {
+    const double t0 = sf_realtime();
     int nt = core->opt.num_thread < 1 ? 1 : core->opt.num_thread;
     if (nt > db->n_rec)
         nt = db->n_rec > 0 ? db->n_rec : 1;
@@ -390,6 +391,7 @@ static void parse_db(core_t *core, db_t *db)
         }
     free(args);
     free(tid);
+    core->parse_time += sf_realtime() - t0;
 }
 
 /* Splits n_rec reads into G contiguous ranges [begin[g], begin[g+1]) holding about the same number of
@@ -436,10 +438,6 @@ static void *gpu_submit_worker(void *p)
 
 void submit_db(core_t *core, db_t *db)
 {
-    const double t0 = sf_realtime();
-    parse_db(core, db);
-    core->parse_time += sf_realtime() - t0;
-
     /* shards: contiguous read ranges with about the same number of samples each */
     const int G = core->num_gpus;
     {
@@ -726,6 +724,7 @@ void collect_db(core_t *core, db_t *db)
 void process_db(core_t *core, db_t *db)
 {
     const double t0 = sf_realtime();
+    parse_db(core, db);
     submit_db(core, db);
     collect_db(core, db);
     core->process_db_time += sf_realtime() - t0;

@@ -21,6 +21,7 @@
 #include <zlib.h>
 
 #include "s5read.h"
+#include "sfinflate.h"
 
 struct sf_s5file {
     FILE *fp;
@@ -274,7 +275,26 @@ static int svb_zd_decode(const uint8_t *in, size_t n_in, sf_rec_t *r)
         return -1;
     int32_t prev = 0;
     int16_t *out = r->raw_signal;
-    for (uint32_t i = 0; i < count; i++) {
+    uint32_t i = 0;
+    /* four values per key byte, branch-free, while a 4-byte load per value cannot run past the input (a key
+     * byte covers at most 16 data bytes, the last load starts at most 12 bytes in and reads 4) */
+    static const uint32_t mask[4] = {0xffu, 0xffffu, 0xffffffu, 0xffffffffu};
+    for (; i + 4 <= count && data + 16 <= end; i += 4) {
+        const unsigned kb = key[i >> 2];
+#define SF_SVB_ONE(j)                                                     \
+        do {                                                              \
+            const unsigned code = (kb >> (2 * (j))) & 3u;                 \
+            uint32_t v;                                                   \
+            memcpy(&v, data, 4);                                          \
+            v &= mask[code];                                              \
+            data += code + 1;                                             \
+            prev += (int32_t)(v >> 1) ^ -(int32_t)(v & 1);                \
+            out[i + (j)] = (int16_t)prev;                                 \
+        } while (0)
+        SF_SVB_ONE(0); SF_SVB_ONE(1); SF_SVB_ONE(2); SF_SVB_ONE(3);
+#undef SF_SVB_ONE
+    }
+    for (; i < count; i++) {
         const unsigned code = (key[i >> 2] >> ((i & 3) * 2)) & 3u;
         if (data + code + 1 > end)
             return -1;
@@ -296,32 +316,52 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
     const uint8_t *p = (const uint8_t *)mem;
     size_t n = bytes;
     if (f->record_press == 1) {
-        /* zlib stream of unknown inflated size: grow until it fits */
-        size_t cap = *scratch_cap ? *scratch_cap : bytes * 4 + 1024;
+        /* zlib stream of unknown inflated size: grow until it fits.  The scratch buffer starts with this
+         * thread's decode tables (sfinflate.h), the inflated record follows. */
+        const size_t hdr = (sizeof(sf_inflater) + 63) & ~(size_t)63;
+        size_t cap = *scratch_cap > hdr ? *scratch_cap - hdr : bytes * 4 + 1024;
+        int use_zlib = 0;
         for (;;) {
-            if (reserve(scratch, scratch_cap, cap))
+            const int fresh = *scratch_cap == 0;
+            if (reserve(scratch, scratch_cap, hdr + cap))
                 return -1;
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, MAX_WBITS) != Z_OK)
-                return -1;
-            zs.next_in = (Bytef *)mem;
-            zs.avail_in = (uInt)bytes;
-            zs.next_out = (Bytef *)*scratch;
-            zs.avail_out = (uInt)*scratch_cap;
-            int rc = inflate(&zs, Z_FINISH);
-            size_t got = zs.total_out;
-            inflateEnd(&zs);
-            if (rc == Z_STREAM_END) {
-                p = (const uint8_t *)*scratch;
+            if (fresh)
+                memset(*scratch, 0, hdr);
+            uint8_t *out = (uint8_t *)*scratch + hdr;
+            const size_t out_cap = *scratch_cap - hdr;
+            size_t got = 0;
+            int rc;
+            if (!use_zlib) {
+                rc = sf_zlib_inflate((sf_inflater *)*scratch, (const uint8_t *)mem, bytes, out, out_cap, &got);
+                if (rc < 0) { /* let zlib have the last word on streams the fast decoder rejects */
+                    use_zlib = 1;
+                    continue;
+                }
+            } else {
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, MAX_WBITS) != Z_OK)
+                    return -1;
+                zs.next_in = (Bytef *)mem;
+                zs.avail_in = (uInt)bytes;
+                zs.next_out = (Bytef *)out;
+                zs.avail_out = (uInt)out_cap;
+                const int zrc = inflate(&zs, Z_FINISH);
+                got = zs.total_out;
+                inflateEnd(&zs);
+                if (zrc == Z_STREAM_END)
+                    rc = 0;
+                else if (zrc == Z_BUF_ERROR || zrc == Z_OK)
+                    rc = 1;
+                else
+                    return -1;
+            }
+            if (rc == 0) {
+                p = out;
                 n = got;
                 break;
             }
-            if (rc == Z_BUF_ERROR || rc == Z_OK) {
-                cap = *scratch_cap * 2;
-                continue;
-            }
-            return -1;
+            cap = out_cap * 2; /* output did not fit */
         }
     }
     size_t o = 0;

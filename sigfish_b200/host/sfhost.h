@@ -124,6 +124,7 @@ typedef struct {
     float *win_len;
     int32_t slot;        /* device slot this batch was submitted to */
     int submitted;
+    int last_batch;      /* set by the loader: the file ended with this batch */
     /* stats */
     int64_t sum_bytes;
     int64_t total_reads;
@@ -160,7 +161,9 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
 db_t *init_db(core_t *core);
 ret_status_t load_db(core_t *core, db_t *db);
 void process_db(core_t *core, db_t *db);
-/* the two halves of process_db: decode + pack + launch on the GPUs / wait + per-read epilogue */
+/* the three parts of process_db: decode the records on the host threads / pack + launch on the GPUs /
+ * wait + per-read epilogue.  dtw_cli.c runs them as pipeline stages on different batches at once. */
+void parse_db(core_t *core, db_t *db);
 void submit_db(core_t *core, db_t *db);
 void collect_db(core_t *core, db_t *db);
 void output_db(core_t *core, db_t *db);

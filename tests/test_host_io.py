@@ -166,3 +166,79 @@ def test_reference_binary_reads_the_blow5_we_write(tmp_path, zl, svb):
     mf = str(tmp_path / "m.txt")
     synth.write_model_file(mf, 6, mean, stdv)
     assert H.run_ref(fa, p, mf) == open(os.path.join(H.GOLDEN, "paf", "dna_sp1_default.paf")).read()
+
+
+# ---- sfinflate.c: the record decoder must agree with zlib byte for byte ----
+
+def _inflater(host):
+    host.sf_zlib_inflate.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    host.sf_zlib_inflate.restype = C.c_int
+    state = C.create_string_buffer(1 << 16)  # sizeof(sf_inflater) < 32 KB, zero-initialised
+
+    def run(data, cap):
+        out = C.create_string_buffer(max(cap, 1))
+        n = C.c_size_t(0)
+        rc = host.sf_zlib_inflate(state, data, len(data), out, cap, C.byref(n))
+        return rc, (out.raw[:n.value] if rc == 0 else b"")
+    return run
+
+
+def _payload(rng, kind, n):
+    if kind == 0:
+        return rng.integers(0, 256, n, dtype=np.uint8).tobytes()          # incompressible: stored / near-flat codes
+    if kind == 1:
+        return rng.integers(0, 4, n, dtype=np.uint8).tobytes()            # short codes
+    if kind == 2:
+        return bytes(n)                                                   # one long run: maximal matches, distance 1
+    if kind == 3:
+        return (np.cumsum(rng.integers(-3, 4, n)) & 255).astype(np.uint8).tobytes()
+    if kind == 4:
+        base = rng.integers(0, 256, max(1, n // 7), dtype=np.uint8).tobytes()
+        return (base * 8)[:n]                                             # long-distance matches
+    p = 1.0 / (np.arange(256) + 1.0) ** 2.2                               # long tail: codes beyond the first-level table
+    return rng.choice(np.arange(256, dtype=np.uint8), n, p=p / p.sum()).tobytes()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_inflate_matches_zlib_on_all_block_types(host, seed):
+    import zlib
+    run = _inflater(host)
+    rng = np.random.default_rng(seed)
+    for it in range(250):
+        n = int(rng.choice([0, 1, 2, 7, 64, 1000, 9000, 70000, 200000]))
+        raw = _payload(rng, int(rng.integers(0, 6)), n)
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, int(rng.integers(9, 16)), 8, strat)
+        comp = co.compress(raw[:n // 2]) + (co.flush(zlib.Z_FULL_FLUSH) if rng.random() < .3 else b"") + \
+            co.compress(raw[n // 2:]) + co.flush()
+        rc, got = run(comp, n + int(rng.integers(0, 40)))
+        assert rc == 0 and got == raw, (seed, it, n, strat)
+        if n > 0:  # output buffer too small is reported, never overrun
+            assert run(comp, int(rng.integers(0, n)))[0] == 1
+        # corrupted and truncated streams: rejected, or (if the damage is harmless) the same bytes zlib gives
+        bad = bytearray(comp)
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        if rng.random() < .3:
+            bad = bad[:int(rng.integers(0, len(bad) + 1))]
+        rc, got = run(bytes(bad), n + 64)
+        assert rc in (0, 1, -1)
+        if rc == 0:
+            assert got == zlib.decompress(bytes(bad))
+
+
+def test_blow5_records_decode_identically_with_every_codec_combination(host, tmp_path):
+    """zlib on / off x svb-zd on / off, signals with the extreme deltas (4-byte svb codes) and lengths that
+    are not a multiple of four (the tail of the fast svb loop)"""
+    rng = np.random.default_rng(11)
+    sigs = [rng.integers(-32768, 32768, size=int(n), dtype=np.int16) for n in (0, 1, 2, 3, 4, 5, 17, 1023, 4096, 9001)]
+    sigs += [np.cumsum(rng.integers(-40, 41, size=6000)).astype(np.int16), np.full(3000, -32768, dtype=np.int16)]
+    ids = [f"r{i}" for i in range(len(sigs))]
+    for zl in (True, False):
+        for svb in (True, False):
+            p = str(tmp_path / f"c_{int(zl)}{int(svb)}.blow5")
+            synth.write_blow5(p, ids, sigs, record_zlib=zl, signal_svb=svb)
+            recs = read_all(host, p)[0]
+            assert [r[0] for r in recs] == ids
+            for r, s in zip(recs, sigs):
+                assert np.array_equal(r[5], s)
