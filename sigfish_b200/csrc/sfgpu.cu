@@ -266,7 +266,13 @@ template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cuda
     const int grid = (a.n_reads + warps - 1) / warps;
     if constexpr (R == 8) { // pairing exists for q = 250 / 256 only, i.e. R = 8 in the warp-per-read layout
         if (pair) {
+            // the reads the pair kernel aligned are traced two per warp; the others by the general kernel
             sf_trace_kernel<R, STD, 16><<<grid, warps * 32, 0, st>>>(a);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                return e;
+            const int units = (a.n_reads + 1) / 2;
+            sf_trace_pair_kernel<16, STD><<<(units + warps - 1) / warps, warps * 32, 0, st>>>(a);
             return cudaGetLastError();
         }
     }
@@ -426,12 +432,14 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ta.ckpt = s.d_ckpt;
         ta.ck_per_read = c->ck_per_read;
         ta.ck_floats = c->ck_floats;
+        ta.list_full = s.d_list_full;
+        ta.n_full = s.d_counts;
         ta.hits = s.d_hits;
         ta.min_window = c->min_window;
         cudaError_t e = cudaErrorInvalidValue;
         SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st, c->R2 > 0)));
         SF_CUDA(c, e);
-        s.timing.other_launches++;
+        s.timing.other_launches += c->R2 > 0 ? 2 : 1;
     }
     SF_CUDA(c, cudaEventRecord(s.ev[4], st));
     if (n > 0) {
