@@ -49,9 +49,9 @@ def main():
         lm, _ = synth.make_model(k)
         seq = synth.random_sequence(29903, rng)
         sigs, _ = synth.simulate_reads([seq], k, lm, n_reads, seed=5, bases_per_read=450)
-        ctx = capi.Context(lm, k)
+        ctx = capi.Context(lm, k, no_pairing=nopair)
         ctx.set_ref([seq])
-        run("C2 30kb DNA q250", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
+        run(f"C2 30kb DNA q250{' nopair' if nopair else ''}", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
         ctx.close()
     if "c4" in which:
         k = 9
