@@ -550,6 +550,10 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_p
             out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
         }
     }
+    // This grid was released early by sf_dtw_score_kernel (griddepcontrol.launch_dependents).  The kernels behind it
+    // in the stream read the results of BOTH; they are ordered behind this grid only, so this grid must not
+    // complete before its prerequisite has completed and flushed: wait for it here, after the work.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // Splits the reads of a batch into those with exactly q_full events (pair kernel; flagged with status bit 5)

@@ -34,6 +34,7 @@ struct sf_s5file {
     int n_attr;
     char **attr_name;
     char ***attr_val;
+    uint32_t *attr_width; /* values allocated for attribute i (the read-group count when its line was read) */
     char *line; /* ASCII line buffer */
     size_t line_cap;
     char errmsg[256];
@@ -53,15 +54,35 @@ static int hdr_add_line(sf_s5file_t *f, char *line)
         return 0;
     f->attr_name = (char **)realloc(f->attr_name, sizeof(char *) * (f->n_attr + 1));
     f->attr_val = (char ***)realloc(f->attr_val, sizeof(char **) * (f->n_attr + 1));
+    f->attr_width = (uint32_t *)realloc(f->attr_width, sizeof(uint32_t) * (f->n_attr + 1));
     f->attr_name[f->n_attr] = strdup(name);
-    char **vals = (char **)calloc(f->num_read_groups ? f->num_read_groups : 1, sizeof(char *));
-    for (uint32_t g = 0; g < (f->num_read_groups ? f->num_read_groups : 1); g++) {
+    /* one value per read group; the row keeps its own width, so that a later (malformed) change of the
+     * read-group count cannot make readers index past it */
+    const uint32_t width = f->num_read_groups ? f->num_read_groups : 1;
+    char **vals = (char **)calloc(width, sizeof(char *));
+    if (!vals)
+        return -1;
+    for (uint32_t g = 0; g < width; g++) {
         char *v = strtok_r(NULL, "\t", &save);
-        vals[g] = v ? strdup(v) : NULL;
+        if (!v)
+            break;
+        vals[g] = strdup(v);
     }
     f->attr_val[f->n_attr] = vals;
+    f->attr_width[f->n_attr] = width;
     f->n_attr++;
     return 0;
+}
+
+/* "#num_read_groups" of the text header.  BLOW5 carries the count in its binary header as well: that one wins.
+ * The count is bounded and frozen once the first '@' row has been sized with it. */
+#define SF_S5_MAX_READ_GROUPS 65536u
+static void set_read_groups(sf_s5file_t *f, const char *text)
+{
+    const unsigned long v = strtoul(text, NULL, 10);
+    if (f->binary || f->n_attr > 0 || v == 0 || v > SF_S5_MAX_READ_GROUPS)
+        return;
+    f->num_read_groups = (uint32_t)v;
 }
 
 /* parses the text header held in buf (binary files) */
@@ -74,7 +95,7 @@ static int parse_text_header(sf_s5file_t *f, char *buf)
             hdr_add_line(f, copy);
             free(copy);
         } else if (!strncmp(line, "#num_read_groups\t", 17)) {
-            f->num_read_groups = (uint32_t)strtoul(line + 17, NULL, 10);
+            set_read_groups(f, line + 17);
         }
     }
     return 0;
@@ -101,6 +122,11 @@ sf_s5file_t *sf_s5_open(const char *path, char *err, size_t errcap)
         memcpy(f->ver, head + 6, 3);
         f->record_press = head[9];
         memcpy(&f->num_read_groups, head + 10, 4);
+        if (f->num_read_groups == 0 || f->num_read_groups > SF_S5_MAX_READ_GROUPS) {
+            snprintf(err, errcap, "%s: implausible number of read groups (%u)", path, f->num_read_groups);
+            f->num_read_groups = 1;
+            goto fail;
+        }
         f->signal_press = (f->ver[0] > 0 || f->ver[1] >= 2) ? head[14] : 0;
         if (f->record_press > 1) {
             snprintf(err, errcap, "%s: record compression method %d is not supported (only none/zlib)", path, f->record_press);
@@ -142,7 +168,7 @@ sf_s5file_t *sf_s5_open(const char *path, char *err, size_t errcap)
         if (f->line[0] == '@')
             hdr_add_line(f, f->line);
         else if (!strncmp(f->line, "#num_read_groups\t", 17))
-            f->num_read_groups = (uint32_t)strtoul(f->line + 17, NULL, 10);
+            set_read_groups(f, f->line + 17);
         else if (!strncmp(f->line, "#slow5_version\t", 15)) {
             unsigned a = 0, b = 0, c2 = 0;
             sscanf(f->line + 15, "%u.%u.%u", &a, &b, &c2);
@@ -167,12 +193,13 @@ void sf_s5_close(sf_s5file_t *f)
         fclose(f->fp);
     for (int i = 0; i < f->n_attr; i++) {
         free(f->attr_name[i]);
-        for (uint32_t g = 0; g < (f->num_read_groups ? f->num_read_groups : 1); g++)
+        for (uint32_t g = 0; g < f->attr_width[i]; g++)
             free(f->attr_val[i][g]);
         free(f->attr_val[i]);
     }
     free(f->attr_name);
     free(f->attr_val);
+    free(f->attr_width);
     free(f->line);
     free(f);
 }
@@ -183,7 +210,7 @@ const char *sf_s5_hdr_get(const sf_s5file_t *f, const char *attr, uint32_t read_
         return NULL;
     for (int i = 0; i < f->n_attr; i++)
         if (!strcmp(f->attr_name[i], attr))
-            return f->attr_val[i][read_group];
+            return read_group < f->attr_width[i] ? f->attr_val[i][read_group] : NULL;
     return NULL;
 }
 
@@ -246,8 +273,14 @@ int64_t sf_s5_get_next_mem(sf_s5file_t *f, char **mem, size_t *cap)
     return (int64_t)len;
 }
 
+/* the reference keeps the sample count of a read in an int32 (nsample, src/sigfish.c:339): longer signals are
+ * rejected here instead of being carried as wrapped sizes */
+#define SF_S5_MAX_SAMPLES ((uint64_t)0x7fffffff - 64)
+
 static int rec_reserve_signal(sf_rec_t *r, size_t n)
 {
+    if ((uint64_t)n > SF_S5_MAX_SAMPLES)
+        return -1;
     if (n <= r->cap_signal)
         return 0;
     int16_t *p = (int16_t *)realloc(r->raw_signal, sizeof(int16_t) * (n + 16));
@@ -351,16 +384,18 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
                 inflateEnd(&zs);
                 if (zrc == Z_STREAM_END)
                     rc = 0;
-                else if (zrc == Z_BUF_ERROR || zrc == Z_OK)
-                    rc = 1;
+                else if ((zrc == Z_BUF_ERROR || zrc == Z_OK) && zs.avail_out == 0)
+                    rc = 1; /* output full: grow */
                 else
-                    return -1;
+                    return -1; /* input exhausted with room left (truncated stream) or corrupt data */
             }
             if (rc == 0) {
                 p = out;
                 n = got;
                 break;
             }
+            if (out_cap > ((size_t)1 << 33))
+                return -1; /* no record inflates to more than 2^31 samples */
             cap = out_cap * 2; /* output did not fit */
         }
     }
@@ -370,7 +405,7 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
         return -1;
     memcpy(&idl, p, 2);
     o = 2;
-    if (o + idl + 4 + 32 + 8 > n)
+    if ((size_t)idl + 4 + 32 + 8 > n - o)
         return -1;
     free(r->read_id);
     r->read_id = (char *)malloc((size_t)idl + 1);
@@ -385,14 +420,14 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
     uint64_t len;
     memcpy(&len, p + o, 8); o += 8;
     if (f->signal_press == 0) {
-        if (o + len * 2 > n)
+        if (len > (n - o) / 2) /* no arithmetic on len before this: it comes from the file */
             return -1;
         if (rec_reserve_signal(r, (size_t)len))
             return -1;
         memcpy(r->raw_signal, p + o, (size_t)len * 2);
         r->len_raw_signal = len;
     } else {
-        if (o + len > n)
+        if (len > n - o)
             return -1;
         if (svb_zd_decode(p + o, (size_t)len, r))
             return -1;
@@ -426,6 +461,9 @@ static int parse_ascii(char *line, sf_rec_t *r)
     r->range = strtod(col[4], NULL);
     r->sampling_rate = strtod(col[5], NULL);
     const uint64_t len = strtoull(col[6], NULL, 10);
+    /* n samples take at least 2n - 1 characters ("d,d,...,d") */
+    if (len > SF_S5_MAX_SAMPLES || len > (strlen(col[7]) + 1) / 2 + 1)
+        return -1;
     if (rec_reserve_signal(r, (size_t)len))
         return -1;
     const char *q = col[7];

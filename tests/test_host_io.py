@@ -272,3 +272,114 @@ def test_real_blow5_of_the_reference_decodes_to_the_golden_signals(host, name):
         assert rc == 0 and got == want
         n += 1
     assert n == len(ids)
+
+
+def _blow5_with_record(path, rec_bytes, record_zlib, signal_svb, hdr_extra=b"", num_groups=1):
+    """a BLOW5 v0.2.0 file holding one hand-made record"""
+    import struct
+    import zlib
+    hdr = (b"@experiment_type\tgenomic_dna\n@sequencing_kit\tsqk-lsk109\n" + hdr_extra +
+           b"#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n"
+           b"#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n")
+    head = b"BLOW5\x01" + bytes([0, 2, 0]) + bytes([1 if record_zlib else 0]) + struct.pack("<I", num_groups) + \
+        bytes([1 if signal_svb else 0])
+    if record_zlib and rec_bytes is not None:
+        rec_bytes = zlib.compress(rec_bytes)
+    with open(path, "wb") as f:
+        f.write(head + b"\x00" * (64 - len(head)) + struct.pack("<I", len(hdr)) + hdr)
+        if rec_bytes is not None:
+            f.write(struct.pack("<Q", len(rec_bytes)) + rec_bytes)
+        f.write(b"5WOLB")
+
+
+def _parse_first(L, path):
+    err = C.create_string_buffer(512)
+    f = L.sf_s5_open(path.encode(), err, 512)
+    assert f, err.value
+    mem, cap = C.c_void_p(), C.c_size_t(0)
+    scratch, scap = C.c_void_p(), C.c_size_t(0)
+    rec = SfRec()
+    n = L.sf_s5_get_next_mem(f, C.byref(mem), C.byref(cap))
+    assert n > 0
+    rc = L.sf_s5_parse(f, mem, n, C.byref(rec), C.byref(scratch), C.byref(scap))
+    L.sf_s5_close(f)
+    return rc, rec
+
+
+@pytest.mark.parametrize("record_zlib", [False, True])
+@pytest.mark.parametrize("signal_svb", [False, True])
+@pytest.mark.parametrize("length", [1 << 63, (1 << 64) - 1, (1 << 63) + 7, 1 << 40, 1 << 32])
+def test_malformed_record_lengths_are_rejected(host, tmp_path, record_zlib, signal_svb, length):
+    """a record whose len_raw_signal field wraps every size computation: must be refused, never
+    reported as parsed with a wrapped buffer"""
+    import struct
+    rid = b"evil"
+    body = struct.pack("<H", len(rid)) + rid + struct.pack("<I", 0) + struct.pack("<dddd", 8192.0, 10.0, 1402.0, 4000.0) + \
+        struct.pack("<Q", length) + b"\x01\x02\x03\x04\x05\x06\x07\x08"
+    p = str(tmp_path / "evil.blow5")
+    _blow5_with_record(p, body, record_zlib, signal_svb)
+    rc, _ = _parse_first(host, p)
+    assert rc != 0
+
+
+def test_malformed_svb_count_and_truncated_zlib_are_rejected(host, tmp_path):
+    import struct
+    import zlib
+    rid = b"evil"
+    pre = struct.pack("<H", len(rid)) + rid + struct.pack("<I", 0) + struct.pack("<dddd", 8192.0, 10.0, 1402.0, 4000.0)
+    # svb-zd stream announcing 2^32-1 samples in 12 bytes
+    svb = struct.pack("<I", 0xffffffff) + b"\x00" * 8
+    p = str(tmp_path / "svb.blow5")
+    _blow5_with_record(p, pre + struct.pack("<Q", len(svb)) + svb, False, True)
+    assert _parse_first(host, p)[0] != 0
+    # a zlib stream cut short: must fail instead of doubling the output buffer for ever
+    good = pre + struct.pack("<Q", 64) + np.arange(64, dtype=np.int16).tobytes()[:128]
+    z = zlib.compress(pre + struct.pack("<Q", 4000) + np.arange(4000, dtype=np.int16).tobytes())
+    with open(str(tmp_path / "cut.blow5"), "wb") as f:
+        head = b"BLOW5\x01" + bytes([0, 2, 0, 1]) + struct.pack("<I", 1) + bytes([0])
+        hdr = b"@experiment_type\tgenomic_dna\n#read_id\n"
+        f.write(head + b"\x00" * (64 - len(head)) + struct.pack("<I", len(hdr)) + hdr)
+        cut = z[:len(z) // 2]
+        f.write(struct.pack("<Q", len(cut)) + cut + b"5WOLB")
+    assert _parse_first(host, str(tmp_path / "cut.blow5"))[0] != 0
+    del good
+    # ASCII: a length field far larger than the signal column
+    s5 = str(tmp_path / "evil.slow5")
+    with open(s5, "w") as f:
+        f.write("#slow5_version\t0.2.0\n#num_read_groups\t1\n@experiment_type\tgenomic_dna\n"
+                "#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n"
+                "#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n"
+                "evil\t0\t8192\t10\t1402\t4000\t9223372036854775808\t1,2,3\n")
+    assert _parse_first(host, s5)[0] != 0
+
+
+def test_header_read_group_count_cannot_grow_after_attributes(host, tmp_path):
+    """'#num_read_groups' after '@' rows (or disagreeing with the binary header) must not widen the rows that
+    sf_s5_hdr_get / sf_s5_close index"""
+    import struct
+    rid = b"r0"
+    body = struct.pack("<H", len(rid)) + rid + struct.pack("<I", 0) + struct.pack("<dddd", 8192.0, 10.0, 1402.0, 4000.0) + \
+        struct.pack("<Q", 2) + np.array([5, 6], np.int16).tobytes()
+    p = str(tmp_path / "g.blow5")
+    _blow5_with_record(p, body, False, False, hdr_extra=b"#num_read_groups\t4000000\n@late\tx\n")
+    err = C.create_string_buffer(512)
+    f = host.sf_s5_open(p.encode(), err, 512)
+    assert f, err.value
+    assert host.sf_s5_hdr_get(f, b"sequencing_kit", 0) == b"sqk-lsk109"
+    for g in (1, 2, 1000, 3999999):
+        assert host.sf_s5_hdr_get(f, b"sequencing_kit", g) is None
+        assert host.sf_s5_hdr_get(f, b"late", g) is None
+    host.sf_s5_close(f)
+    # the same in a text file
+    s5 = str(tmp_path / "g.slow5")
+    with open(s5, "w") as fo:
+        fo.write("#slow5_version\t0.2.0\n#num_read_groups\t1\n@experiment_type\trna\n#num_read_groups\t70000\n@late\tx\n"
+                 "#char*\tuint32_t\n#read_id\tread_group\n")
+    f = host.sf_s5_open(s5.encode(), err, 512)
+    assert f, err.value
+    assert host.sf_s5_hdr_get(f, b"experiment_type", 0) == b"rna"
+    assert host.sf_s5_hdr_get(f, b"experiment_type", 5) is None
+    host.sf_s5_close(f)
+    # an absurd count in the binary header is refused at open
+    _blow5_with_record(p, body, False, False, num_groups=0x7fffffff)
+    assert not host.sf_s5_open(p.encode(), err, 512)
