@@ -47,6 +47,17 @@ def random_sequence(n: int, rng: np.random.Generator) -> bytes:
     return _BASES[rng.integers(0, 4, size=n)].tobytes()
 
 
+def transcriptome(n: int, seed: int, lo: int = 400, hi: int = 4000):
+    """n seeded random transcripts with lengths uniform in [lo, hi] (BASELINE.json configs[4]: many short
+    references); returns (names, sequences)"""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(lo, hi + 1, size=n)
+    flat = _BASES[rng.integers(0, 4, size=int(lens.sum()))]
+    offs = np.zeros(n + 1, dtype=np.int64)
+    offs[1:] = np.cumsum(lens)
+    return [f"tx{i:06d}" for i in range(n)], [flat[offs[i]:offs[i + 1]].tobytes() for i in range(n)]
+
+
 def write_fasta(path: str, names, seqs, width: int = 80) -> None:
     with open(path, "w") as f:
         for name, s in zip(names, seqs):

@@ -131,7 +131,24 @@ CASES = {
     "rna_tail24_auto": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA, 250, -1),
     "rna_tail24_auto_dtw_std": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA | H.F_DTW, 250, -1),
     "rna_tail24_p50": ("synth_rna_tail24", "rnasequin", 5, H.F_RNA, 250, 50),
+    # BASELINE.json configs[4] in small: RNA004 (9-mer RNA model, kit sqk-rna004 => pore auto-detected,
+    # sigfish.c:62-64,123-135), a seeded transcriptome of 2000 transcripts of 400-4000 nt (not stored: regenerated
+    # from its seed, checksum in cases.json), reads from the 3' ends
+    "rna004_tx2000_invert": ("synth_rna004_24", "gen_rna004_tx2000", 9, H.F_RNA | H.F_INV, 250, 50),
+    "rna004_tx2000_default": ("synth_rna004_24", "gen_rna004_tx2000", 9, H.F_RNA, 250, 50),
+    "rna004_tx2000_invert_full_ref": ("synth_rna004_24", "gen_rna004_tx2000", 9, H.F_RNA | H.F_INV | H.F_REF, 250, 50),
+    "rna004_tx2000_dtw_std": ("synth_rna004_24", "gen_rna004_tx2000", 9, H.F_RNA | H.F_DTW, 250, 50),
+    "rna004_tail16_auto": ("synth_rna004_tail16", "gen_rna004_tx2000", 9, H.F_RNA, 250, -1),
 }
+
+# per-case extras: the sequencing_kit written into the read file's header and the pore it makes the reference
+# detect (opt.pore_flag: selects the jnn parameter set of -p -1)
+CASE_EXTRA = {c: dict(kit="sqk-rna004", pore=2) for c in CASES if c.startswith("rna004_")}
+# 4.4 M reference columns per read: the single-threaded oracle checks only the first reads of this case (the
+# GPU command line is compared with all golden lines)
+CASE_EXTRA["rna004_tx2000_invert_full_ref"]["oracle_reads"] = 3
+for _c in ("rna004_tx2000_default", "rna004_tx2000_dtw_std", "rna004_tail16_auto"):
+    CASE_EXTRA[_c]["oracle_reads"] = 8  # keeps the CPU suite short; rna004_tx2000_invert runs all 24
 
 
 # name -> (truth PAF, test PAF, options) for `sigfish eval`
@@ -147,7 +164,7 @@ EVAL_CASES = {
 
 SAM_CASES = ["dna_sp1_default", "dna_sp1_from_end", "dna_synth48", "dna_multi_contig", "dna_short_reads", "dna_r10_k9",
              "rna_sequin_default", "rna_sequin_invert", "rna_sequin_full_ref", "rna_sequin_q500_auto",
-             "rna_tail24_auto", "rna_synth32"]
+             "rna_tail24_auto", "rna_synth32", "rna004_tx2000_invert", "rna004_tail16_auto"]
 
 
 def main():
@@ -205,6 +222,14 @@ def main():
     save_reads(os.path.join(HERE, "synth_rna_tail24.npz"), [f"synth_tail_{i:04d}" for i in range(24)], sigs,
                [synth.RNA_SCALING] * 24)
 
+    tx_names, tx_seqs = H.case_fasta("gen_rna004_tx2000")
+    sigs, _ = synth.simulate_reads(tx_seqs, 9, models[9][0], 24, seed=17, rna=True, bases_per_read=420)
+    save_reads(os.path.join(HERE, "synth_rna004_24.npz"), [f"synth_rna004_{i:04d}" for i in range(24)], sigs,
+               [synth.RNA_SCALING] * 24)
+    sigs, _ = synth.simulate_rna_reads_with_tail(tx_seqs, 9, models[9][0], 16, seed=18, bases_per_read=500)
+    save_reads(os.path.join(HERE, "synth_rna004_tail16.npz"), [f"synth_rna004_tail_{i:04d}" for i in range(16)], sigs,
+               [synth.RNA_SCALING] * 16)
+
     # 3. golden PAFs from the reference binary
     for k, (mean, stdv) in models.items():
         synth.write_model_file(os.path.join(tmp, f"model_k{k}.txt"), k, mean, stdv)
@@ -213,14 +238,22 @@ def main():
         ids, sg, sc = H.load_reads_npz(os.path.join(HERE, reads + ".npz"))
         s5 = os.path.join(tmp, reads + ".slow5")
         rna = bool(flags & H.F_RNA)
-        synth.write_slow5_ascii(s5, ids, sg, rna=rna, scalings=sc)
+        extra = CASE_EXTRA.get(case, {})
+        s5 = os.path.join(tmp, reads + ("_" + extra["kit"] if extra else "") + ".slow5")
+        synth.write_slow5_ascii(s5, ids, sg, rna=rna, kit=extra.get("kit"), scalings=sc)
         fa = os.path.join(tmp, fasta + ".fa")
-        with gzip.open(os.path.join(HERE, fasta + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
-            shutil.copyfileobj(fi, fo)
+        if fasta in H.GENERATED_FASTA:
+            H.write_case_fasta(fasta, fa)
+        else:
+            with gzip.open(os.path.join(HERE, fasta + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+                shutil.copyfileobj(fi, fo)
         paf = H.run_ref(fa, s5, os.path.join(tmp, f"model_k{k}.txt"), flags=flags, q=q, p=p)
         with open(os.path.join(HERE, "paf", case + ".paf"), "w") as f:
             f.write(paf)
-        summary[case] = dict(reads=reads, fasta=fasta, k=k, flags=flags, q=q, p=p, rows=paf.count("\n"))
+        summary[case] = dict(reads=reads, fasta=fasta, k=k, flags=flags, q=q, p=p, rows=paf.count("\n"), **extra)
+        if fasta in H.GENERATED_FASTA:
+            import hashlib
+            summary[case]["fasta_sha1"] = hashlib.sha1(b"\n".join(H.case_fasta(fasta)[1])).hexdigest()
         print(case, summary[case]["rows"], "rows")
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(summary, f, indent=1, sort_keys=True)
@@ -229,7 +262,8 @@ def main():
     os.makedirs(os.path.join(HERE, "sam"), exist_ok=True)
     for case in SAM_CASES:
         reads, fasta, k, flags, q, p = CASES[case]
-        sam = H.run_ref(os.path.join(tmp, fasta + ".fa"), os.path.join(tmp, reads + ".slow5"),
+        extra = CASE_EXTRA.get(case, {})
+        sam = H.run_ref(os.path.join(tmp, fasta + ".fa"), os.path.join(tmp, reads + ("_" + extra["kit"] if extra else "") + ".slow5"),
                         os.path.join(tmp, f"model_k{k}.txt"), flags=flags, q=q, p=p, extra=["--sam"])
         with open(os.path.join(HERE, "sam", case + ".sam"), "w") as f:
             f.write(sam)

@@ -276,6 +276,48 @@ def read_fasta(path: str):
     return names, seqs
 
 
+# fasta fixtures that are generated from a seed instead of being stored: name -> (transcripts, seed, lo, hi)
+GENERATED_FASTA = {"gen_rna004_tx2000": (2000, 20240, 400, 4000)}
+
+
+def case_fasta(c_or_name):
+    """(names, sequences) of a golden case's reference: a committed .fa.gz, or a seeded transcriptome whose
+    checksum make_golden.py recorded in cases.json"""
+    name = c_or_name if isinstance(c_or_name, str) else c_or_name["fasta"]
+    if name in GENERATED_FASTA:
+        import hashlib
+        from sigfish_b200 import synth
+        n, seed, lo, hi = GENERATED_FASTA[name]
+        names, seqs = synth.transcriptome(n, seed, lo, hi)
+        if not isinstance(c_or_name, str) and "fasta_sha1" in c_or_name:
+            got = hashlib.sha1(b"\n".join(seqs)).hexdigest()
+            assert got == c_or_name["fasta_sha1"], "seeded transcriptome differs from the one the golden PAF was made with"
+        return names, seqs
+    return read_fasta(os.path.join(GOLDEN, name + ".fa.gz"))
+
+
+def write_case_fasta(c_or_name, path: str) -> None:
+    from sigfish_b200 import synth
+    names, seqs = case_fasta(c_or_name)
+    synth.write_fasta(path, names, seqs, width=60)
+
+
+def case_reads(c):
+    return load_reads_npz(os.path.join(GOLDEN, c["reads"] + ".npz"))
+
+
+def case_kit(c):
+    """sequencing_kit header value of the case's read file (selects the pore: src/sigfish.c:52-79)"""
+    if c.get("kit"):
+        return c["kit"]
+    return "sqk-lsk114" if c["k"] == 9 else None
+
+
+def case_oracle_flags(c) -> int:
+    """oracle flag word: the option bits plus the oracle-only RNA004 bit (jnn parameter set)"""
+    return c["flags"] | (0x400 if c.get("pore", 0) == 2 else 0)
+
+
 def load_reads_npz(path: str):
     """fixture written by tests/golden/make_golden.py"""
     z = np.load(path, allow_pickle=False)

@@ -28,11 +28,14 @@ def cli():
 def _inputs(tmp, case, fmt):
     c = CASES[case]
     fa = os.path.join(tmp, "ref.fa")
-    with gzip.open(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
-        shutil.copyfileobj(fi, fo)
-    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, c["reads"] + ".npz"))
+    if c["fasta"] in H.GENERATED_FASTA:
+        H.write_case_fasta(c, fa)
+    else:
+        with gzip.open(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    ids, sigs, sc = H.case_reads(c)
     rna = bool(c["flags"] & H.F_RNA)
-    kit = "sqk-lsk114" if c["k"] == 9 else None
+    kit = H.case_kit(c)
     reads = os.path.join(tmp, "reads." + fmt)
     if fmt == "slow5":
         synth.write_slow5_ascii(reads, ids, sigs, rna=rna, kit=kit, scalings=sc)
@@ -165,7 +168,8 @@ def test_cli_fuzz_matches_oracle_paf_and_sam(cli, tmp_path, seed):
     (incl. -1), contigs and reads; PAF and SAM text must be identical"""
     rng = np.random.default_rng(8000 + seed)
     rna = bool(rng.integers(0, 2))
-    k = 5 if rna else int(rng.choice([6, 9]))
+    k = (9 if seed % 3 == 2 else 5) if rna else int(rng.choice([6, 9]))  # RNA: r9 5-mers and RNA004 9-mers
+    rna004 = rna and k == 9
     flags = 0
     p = int(rng.choice([0, 10, 50, 50, 120]))
     if rna:
@@ -190,12 +194,15 @@ def test_cli_fuzz_matches_oracle_paf_and_sam(cli, tmp_path, seed):
     ids = [f"r{i}" for i in range(len(sigs))]
     fa, s5, mf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.blow5"), str(tmp_path / "model.txt")
     synth.write_fasta(fa, names, seqs)
-    synth.write_blow5(s5, ids, sigs, rna=rna, kit="sqk-lsk114" if k == 9 else None, scalings=scs)
+    synth.write_blow5(s5, ids, sigs, rna=rna, kit="sqk-rna004" if rna004 else ("sqk-lsk114" if k == 9 else None), scalings=scs)
     synth.write_model_file(mf, k, mean, stdv)
     c = dict(q=q, p=p, flags=flags)
-    out, _ = _run(cli, c, fa, s5, mf, ["-K", "3"])
-    assert out == H.oracle_paf(names, seqs, mean, k, ids, sigs, scs, flags, q, p), (flags, q, p)
+    oflags = flags | (0x400 if rna004 else 0)
+    out, err = _run(cli, c, fa, s5, mf, ["-K", "3"])
+    if rna004:
+        assert "--pore rna004 was set automatically" in err
+    assert out == H.oracle_paf(names, seqs, mean, k, ids, sigs, scs, oflags, q, p), (flags, q, p)
     if not flags & H.F_DTW:
         out, _ = _run(cli, c, fa, s5, mf, ["--sam"])
         out = "".join(l for l in out.splitlines(keepends=True) if not l.startswith("@PG"))
-        assert out == H.oracle_sam(names, seqs, mean, k, ids, sigs, scs, flags, q, p), (flags, q, p)
+        assert out == H.oracle_sam(names, seqs, mean, k, ids, sigs, scs, oflags, q, p), (flags, q, p)
