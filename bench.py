@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU baseline sample (0: one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warm-blocks", type=int, default=0, help="experiment knob: warm-up of a piece in 64-column blocks (0: 2q columns)")
+    ap.add_argument("--piece-periods", type=int, default=0, help="experiment knob: piece length in checkpoint periods (0: per batch, <0: no splitting)")
     args = ap.parse_args()
     # the JSON line is the only thing that may reach stdout: libraries that write to fd 1 (NCCL prints its version
     # there) are sent to stderr, and the line itself goes to the saved descriptor
@@ -217,7 +219,8 @@ def main():
     from sigfish_b200 import synth
     mean, stdv = synth.make_model(KMER)
     seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
-    ctx = capi.Context(mean, KMER, flags=0, query_size=Q, prefix_size=P, device=local, n_slots=2)
+    ctx = capi.Context(mean, KMER, flags=0, query_size=Q, prefix_size=P, device=local, n_slots=2,
+                       warm_blocks=args.warm_blocks, piece_periods=args.piece_periods)
     ctx.set_ref([seq])
     # a task (one read x one strand of the 1 Mb contig) runs ~190 ms, so the batch is sized to whole waves of
     # resident warps; four waves per step (measured per-wave time: 1 wave 197 ms, 2: 209, 3: 196, 4: 193, 6: 191, 8: 194)
@@ -253,6 +256,7 @@ def main():
         trc += t.trace_ms
         cells = t.cells
         launches += t.dtw_launches + t.other_launches
+        split = {"tasks_per_read": t.tasks_per_read, "piece_columns": t.piece_blocks * 64, "redone_pieces_last_step": t.redone_pieces}
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     sampler.stop_flag = True
@@ -303,6 +307,7 @@ def main():
                        "batch": "four full waves of (read, strand) DTW tasks per step (4 x sfgpu_wave_reads)" if args.reads <= 0 else "--reads",
                        "l2": "256 MB buffer written between timed iterations (L2 flush)",
                        "parallelism": f"reads sharded over {world} GPU(s), reference replicated, no collective"},
+            "split": split,
             "stage_ms": {"events": evt_ms, "dtw": dtw_ms, "merge_trace": trc_ms, "wall_per_step_incl_flush": wall_step},
             "e2e": {"value": job_cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "reads_per_s": job_reads / (e2e_ms * 1e-3)},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFGPU_ABI_VERSION 1
+#define SFGPU_ABI_VERSION 2
 
 /* option bits: identical to the reference's opt.flag (src/sigfish.h:30-39) */
 #define SFGPU_RNA 0x001 /* --rna       */
@@ -54,7 +54,8 @@ typedef struct {
     int32_t kmer_size;    /* core->kmer_size */
     int32_t n_slots;      /* batches in flight (double buffering); 0 -> 2 */
     int32_t pore;         /* opt.pore_flag: 0 r9, 1 r10, 2 rna004 (only selects the jnn parameters) */
-    int32_t reserved[5];  /* test knobs, keep 0: [0] checkpoint spacing, [1] restart window, [3] 1 = no read pairing */
+    int32_t reserved[5];  /* test knobs, keep 0: [0] checkpoint spacing, [1] restart window, [2] warm-up blocks of a piece,
+                             [3] 1 = no read pairing, [4] piece length in checkpoint periods (< 0: never split) */
 } sfgpu_opt_t;
 
 /* per-read output of the device stages: what normalise_single() leaves in db->qstart/qend
@@ -80,6 +81,10 @@ typedef struct {
     double cells;         /* sum over reads of qlen * total reference columns */
     int64_t samples;      /* raw samples uploaded */
     int32_t dtw_launches, other_launches;
+    int32_t tasks_per_read;  /* DTW tasks one read was cut into (groups + pieces of long segments) */
+    int32_t piece_blocks;    /* piece length the batch used, in blocks of 64 columns (0: segments not split) */
+    int32_t redone_pieces;   /* pieces recomputed because their warm-up front did not verify */
+    int32_t pad;
 } sfgpu_timing_t;
 
 /* number of CUDA devices with compute capability 10.x */

@@ -45,7 +45,8 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("events_ms", C.c_float), ("dtw_ms", C.c_float),
                 ("trace_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("cells", C.c_double), ("samples", C.c_int64), ("dtw_launches", C.c_int32),
-                ("other_launches", C.c_int32)]
+                ("other_launches", C.c_int32), ("tasks_per_read", C.c_int32), ("piece_blocks", C.c_int32),
+                ("redone_pieces", C.c_int32), ("pad", C.c_int32)]
 
 
 _lib = None
@@ -99,14 +100,17 @@ class Context:
 
     def __init__(self, level_mean: np.ndarray, kmer_size: int, flags: int = 0, query_size: int = 250,
                  prefix_size: int = 50, device: int = 0, n_slots: int = 2, ck_min_cols: int = 0,
-                 min_window: int = 0, pore: int = 0, no_pairing: bool = False):
+                 min_window: int = 0, pore: int = 0, no_pairing: bool = False, warm_blocks: int = 0,
+                 piece_periods: int = 0):
         L = lib()
         self._h = C.c_void_p()
         self.opt = Opt(device=device, flags=flags, query_size=query_size, prefix_size=prefix_size,
                        kmer_size=kmer_size, n_slots=n_slots, pore=pore)
         self.opt.reserved[0] = ck_min_cols  # test knob: checkpoint segments longer than this
         self.opt.reserved[1] = min_window   # test knob: restart distance of the start-coordinate pass
+        self.opt.reserved[2] = warm_blocks  # test knob: warm-up of a piece of a split segment, in 64-column blocks
         self.opt.reserved[3] = int(no_pairing)  # test knob: one read per warp even for q = 250 / 256
+        self.opt.reserved[4] = piece_periods  # test knob: piece length in checkpoint periods (< 0: never split)
         lm = np.ascontiguousarray(level_mean, dtype=np.float32)
         assert lm.shape[0] == 4 ** kmer_size
         rc = L.sfgpu_create(C.byref(self._h), C.byref(self.opt), _ptr(lm))

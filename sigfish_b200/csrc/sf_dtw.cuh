@@ -38,13 +38,14 @@ struct sf_dtw_args {
     const float *stream;
     const sf_seg *segs;
     const sf_group *groups;
-    const int32_t *order;   // group ids, longest first
-    int32_t n_groups;
+    const sf_piece *pieces; // the tasks of one read: whole groups and pieces of long segments (one split level)
+    const int32_t *order;   // piece ids, longest first
+    int32_t n_pieces;
     int32_t n_reads;
     const float *queries;   // [n_reads][q_cap]
     const sf_readinfo *info;
     int32_t q_cap;
-    sf_taskres *res;        // [n_reads][n_groups]
+    sf_taskres *res;        // [n_reads][n_pieces]
     float *ckpt;            // [(read * ck_per_read + ck_prefix + k)][R+2][32]
     int64_t ck_per_read;
     int32_t ck_floats;      // floats per checkpoint (max over the layouts in use)
@@ -53,6 +54,15 @@ struct sf_dtw_args {
     const int32_t *list;
     const int32_t *n_list;
     int32_t q_full;         // pair kernel: every listed read has exactly this query length
+    // pieces: warm fronts [(read * n_warm + widx)][ck_floats] and the warm-up length
+    float *warm;
+    int32_t n_warm;
+    int32_t warm_blocks;
+    // FIX instantiations: first piece of each (read, split group) whose fronts differ (0x7fffffff: none)
+    const int32_t *first_bad;   // [n_reads][n_split]
+    int32_t n_split;
+    const int32_t *split_first; // [n_split] piece id of piece 0
+    const int32_t *split_count; // [n_split] pieces of the group
 };
 
 // ring (float2 x 128) + last-row buffer (2 values per macro-step; 2R in the generic block)
@@ -189,7 +199,238 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
     }
 }
 
-template <int R, bool STD>
+// do the fronts of piece `pidx` agree: the warm front it reached at its boundary against the checkpoint its
+// predecessor wrote there?  n_f = floats of the layout the read ran in.  Warp-uniform result.
+__device__ __forceinline__ bool sf_fronts_equal(const sf_dtw_args &a, const int read, const int pidx, const int lane, const int n_f)
+{
+    const sf_piece pc = a.pieces[pidx];
+    const sf_group grp = a.groups[pc.gid];
+    const unsigned *w = reinterpret_cast<const unsigned *>(a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats);
+    const unsigned *f = reinterpret_cast<const unsigned *>(
+        a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + pc.b0 / grp.ck_every - 1) * (size_t)a.ck_floats);
+    bool ne = false;
+    for (int i = lane; i < n_f; i += 32)
+        ne |= w[i] != f[i];
+    return !__any_sync(0xffffffffu, ne);
+}
+
+// One (read, piece) task of the warp-per-read layout.  RESUME: start at the piece's boundary from the checkpoint the
+// predecessor left there (redo of a piece whose warm front did not verify) instead of warming up.
+template <int R, bool STD, bool RESUME>
+__device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int read, const int pidx, const int lane,
+                                              float2 *ring, float *last)
+{
+    const unsigned full = 0xffffffffu;
+    const sf_piece pc = a.pieces[pidx];
+    const sf_group grp = a.groups[pc.gid];
+    sf_taskres *out = a.res + (size_t)read * a.n_pieces + pidx;
+    const int qlen = a.info[read].qlen;
+    if (qlen <= 0) {
+        if (lane == 0) {
+            out->s1 = SF_INF; out->s2 = SF_INF; out->seg = -1; out->chunk = 0; out->pos = -1;
+            out->hmin = SF_INF; out->hpos = -1; out->hchunk = -1; out->tmin = SF_INF; out->tpos = -1; out->tchunk = -2;
+        }
+        return;
+    }
+    const int lq = (qlen - 1) / R; // lane holding the last query row
+    const int rq = (qlen - 1) % R; // its register
+    const bool is_lq = lane == lq;
+    const bool fast = rq == sf_fast_rq(R); // warp-uniform
+    const int nz = lane != 0;
+    // bit 0: has a predecessor, bit 1: has a successor, bit 2: the head edge is still to come
+    int pflags = pc.flags | ((pc.flags & 1) << 2);
+
+    const float *y = a.stream + grp.begin;
+    const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
+    // the last column (n_pos-1) is in pair (n_pos-1)/2 and reaches lane lq lq macro-steps later
+    const int b_end = (pflags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
+    const int b_first = RESUME ? pc.b0 : ((pflags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
+
+    // query rows of this lane; rows past qlen are padding (finite, never read back)
+    float x[R], L[R];
+    const float *q = a.queries + (size_t)read * a.q_cap;
+    float botA = SF_INF, botB = SF_INF;
+    float dprev = (lane == 0 && !STD) ? 0.0f : SF_INF;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row = lane * R + r;
+        x[r] = row < qlen ? q[row] : 0.0f;
+        L[r] = SF_INF;
+    }
+    if (RESUME) {
+        const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + pc.b0 / grp.ck_every - 1) * (size_t)a.ck_floats;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            L[r] = c[r * 32 + lane];
+        dprev = c[R * 32 + lane];
+        botA = c[(R + 1) * 32 + lane];
+        botB = L[R - 1];
+    }
+
+    __syncwarp();
+    // ring: block b (pairs 32b .. 32b+31) lives at slots (b&1)*32 + j and again 64 slots later; the block "before"
+    // the first one reads as +INF columns, and so does the first column of a warm-up (the virtual column -1 of the
+    // windowed recurrence); a resumed task continues inside the segment and needs the real previous block
+    {
+        const int c0 = SF_BLOCK_COLS * b_first + 2 * lane, c1 = c0 + 1;
+        float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
+        if (!RESUME && b_first > 0 && lane == 0)
+            v.x = SF_INF;
+        float2 pv = make_float2(SF_INF, SF_INF);
+        if (RESUME)
+            pv = make_float2(c0 - SF_BLOCK_COLS < n_pos ? y[c0 - SF_BLOCK_COLS] : SF_INF,
+                             c1 - SF_BLOCK_COLS < n_pos ? y[c1 - SF_BLOCK_COLS] : SF_INF);
+        const int cur = (b_first & 1) * 32 + lane, prv = ((b_first & 1) ^ 1) * 32 + lane;
+        ring[cur] = v; ring[cur + 64] = v;
+        ring[prv] = pv; ring[prv + 64] = pv;
+    }
+    __syncwarp();
+
+    // chunk bookkeeping (warp-uniform)
+    int si = grp.seg0;
+    const int si_end = grp.seg0 + grp.nseg;
+    sf_seg seg = a.segs[si];
+    int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
+    int chunk = 0;
+    int clo = STD ? hi - 1 : lo;
+    int ck = 0;
+    if (pflags & 3) { // a piece of a split segment (single-segment group, never STD): the last row of its own
+                      // blocks [b0, b1) is columns [64 b0 - 2 lq, 64 b1 - 2 lq)
+        if (pflags & 2)
+            hi = min(hi, SF_BLOCK_COLS * pc.b1 - 2 * lq);
+        if (pflags & 1) {
+            clo = SF_BLOCK_COLS * pc.b0 - 2 * lq;
+            chunk = (clo - lo) / qlen;
+            ck = pc.b0 / grp.ck_every;
+        }
+    }
+    int chi = STD ? hi : min(lo + (chunk + 1) * qlen, hi);
+    float rmin = SF_INF; // per lane running minimum of the open chunk
+    int rpos = -1;
+    float s1 = SF_INF, s2 = SF_INF;
+    int bseg = -1, bchunk = 0, bpos = -1;
+
+    for (int b = b_first; b < b_end; b++) {
+        // prefetch the next 64 reference events; published after the 32 macro-steps below
+        const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
+        const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
+        const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
+        const float2 *yb = ring + ((b & 1) ? 32 : 64) - lane;
+
+        if (fast)
+            sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
+        else
+            sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
+        __syncwarp();
+
+        // ---- last-row chunk minima (sigfish.c:891-901): this block produced the last row of columns
+        //      p0 .. p0+63; lane l looks at p0+2l and p0+2l+1 ----
+        {
+            const int p0 = SF_BLOCK_COLS * b - 2 * lq;
+            const int pos0 = p0 + 2 * lane;
+            float v0, v1;
+            if (fast) {
+                const float2 v = *reinterpret_cast<const float2 *>(last + 2 * lane);
+                v0 = v.x; v1 = v.y;
+            } else {
+                const float2 v = *reinterpret_cast<const float2 *>(last + (lane * R + rq) * 2);
+                v0 = v.x; v1 = v.y;
+            }
+            for (;;) {
+                if (pos0 >= clo && pos0 < chi && v0 < rmin) {
+                    rmin = v0;
+                    rpos = pos0;
+                }
+                if (pos0 + 1 >= clo && pos0 + 1 < chi && v1 < rmin) {
+                    rmin = v1;
+                    rpos = pos0 + 1;
+                }
+                if (chi > p0 + SF_BLOCK_COLS)
+                    break;
+                // chunk complete: first strict minimum = smallest value, then smallest column
+                float m = rmin;
+                int mp = rpos;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float om = __shfl_xor_sync(full, m, o);
+                    const int op = __shfl_xor_sync(full, mp, o);
+                    if (om < m || (om == m && (unsigned)op < (unsigned)mp)) {
+                        m = om;
+                        mp = op;
+                    }
+                }
+                if (pflags & 4) { // the chunk cut by the piece's start: reported apart (head edge)
+                    if (lane == 0) { out->hmin = m; out->hpos = mp >= 0 ? mp - lo : -1; out->hchunk = chunk; }
+                    pflags &= ~4;
+                } else if ((pflags & 2) && chi >= hi) { // the chunk cut by the piece's end (tail edge)
+                    if (lane == 0) { out->tmin = m; out->tpos = mp >= 0 ? mp - lo : -1; out->tchunk = chunk; }
+                } else if (m <= s1) { // update_aln(): a later candidate with an equal score ranks better
+                    s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
+                } else if (m < s2) {
+                    s2 = m;
+                }
+                rmin = SF_INF;
+                rpos = -1;
+                clo = chi;
+                chunk++;
+                if (clo >= hi) {
+                    si++;
+                    chunk = 0;
+                    if (si < si_end) {
+                        seg = a.segs[si];
+                        lo = (int)(seg.off - grp.begin);
+                        hi = lo + seg.rlen;
+                        clo = STD ? hi - 1 : lo;
+                    } else {
+                        clo = 0x7fffffff;
+                        hi = 0x7fffffff;
+                    }
+                }
+                chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
+            }
+        }
+
+        // ---- checkpoint of the skewed wavefront (for the start-coordinate pass; the one at a piece's end is also
+        //      what the next piece's warm front is verified against) ----
+        if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
+            float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                c[r * 32 + lane] = L[r];
+            c[R * 32 + lane] = dprev;
+            c[(R + 1) * 32 + lane] = botA;
+            ck++;
+        }
+        // ---- warm front: the state this piece reached at its boundary ----
+        if (!RESUME && (pflags & 1) && b + 1 == pc.b0) {
+            float *c = a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                c[r * 32 + lane] = L[r];
+            c[R * 32 + lane] = dprev;
+            c[(R + 1) * 32 + lane] = botA;
+        }
+
+        // publish block b+1 of the reference events (overwrites block b-1)
+        {
+            const int slot = ((b + 1) & 1) * 32 + lane;
+            const float2 v = make_float2(yn0, yn1);
+            ring[slot] = v;
+            ring[slot + 64] = v;
+        }
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
+    }
+}
+
+// FIX: the redo pass.  Walks the pieces of every (read, split group) that sf_verify_kernel flagged, from the first
+// piece whose fronts differ: that piece is recomputed from its predecessor's front (which is the full-matrix state
+// by induction), which rewrites the checkpoint at its own end; every later piece is then checked against the
+// front now standing before it and recomputed if it differs.
+template <int R, bool STD, bool FIX = false>
 __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_score_kernel(const sf_dtw_args a)
 {
     extern __shared__ float2 sf_smem2[];
@@ -199,10 +440,11 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
     float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
     const int n_list = a.list ? *a.n_list : a.n_reads;
-    const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)n_list;
+    const unsigned n_tasks = (unsigned)(FIX ? a.n_split : a.n_pieces) * (unsigned)n_list;
     // a kernel launched behind this one with programmatic stream serialisation (the pair kernel: it shares no data
     // with this one) may start as soon as every block of this grid is resident
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!FIX)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     for (;;) {
         unsigned task = 0;
@@ -214,164 +456,20 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
         const int gi = task / (unsigned)n_list;
         const int li = task - gi * n_list;
         const int read = a.list ? a.list[li] : li;
-        const int gid = a.order[gi];
-        const sf_group grp = a.groups[gid];
-        sf_taskres *out = a.res + (size_t)read * a.n_groups + gid;
-        const int qlen = a.info[read].qlen;
-        if (qlen <= 0) {
-            if (lane == 0) {
-                out->s1 = SF_INF; out->s2 = SF_INF; out->seg = -1; out->chunk = 0; out->pos = -1;
+        if (!FIX) {
+            sf_score_task<R, STD, false>(a, read, a.order[gi], lane, ring, last);
+        } else {
+            const int k0 = a.first_bad[(size_t)read * a.n_split + gi];
+            if (k0 == 0x7fffffff)
+                continue;
+            const int p0 = a.split_first[gi], K = a.split_count[gi];
+#pragma unroll 1
+            for (int k = k0; k < K; k++) {
+                if (k > k0 && sf_fronts_equal(a, read, p0 + k, lane, sf_ckpt_floats(R)))
+                    continue;
+                sf_score_task<R, STD, true>(a, read, p0 + k, lane, ring, last);
+                __syncwarp();
             }
-            continue;
-        }
-        const int lq = (qlen - 1) / R; // lane holding the last query row
-        const int rq = (qlen - 1) % R; // its register
-        const bool is_lq = lane == lq;
-        const bool fast = rq == sf_fast_rq(R); // warp-uniform
-        const int nz = lane != 0;
-
-        // query rows of this lane; rows past qlen are padding (finite, never read back)
-        float x[R], L[R];
-        const float *q = a.queries + (size_t)read * a.q_cap;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = lane * R + r;
-            x[r] = row < qlen ? q[row] : 0.0f;
-            L[r] = SF_INF;
-        }
-        float botA = SF_INF, botB = SF_INF;
-        float dprev = (lane == 0 && !STD) ? 0.0f : SF_INF;
-
-        const float *y = a.stream + grp.begin;
-        const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
-        // the last column (n_pos-1) is in pair (n_pos-1)/2 and reaches lane lq lq macro-steps later
-        const int n_blocks = ((n_pos - 1) / 2 + lq + 32) >> 5;
-
-        __syncwarp();
-        // ring: block b (pairs 32b .. 32b+31) lives at slots (b&1)*32 + j and again 64 slots later;
-        // the block "before" block 0 reads as +INF columns
-        {
-            const int c0 = 2 * lane, c1 = c0 + 1;
-            const float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
-            ring[lane] = v; ring[64 + lane] = v;
-            const float2 inf2 = make_float2(SF_INF, SF_INF);
-            ring[32 + lane] = inf2; ring[96 + lane] = inf2;
-        }
-        __syncwarp();
-
-        // chunk bookkeeping (warp-uniform)
-        int si = grp.seg0;
-        const int si_end = grp.seg0 + grp.nseg;
-        sf_seg seg = a.segs[si];
-        int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
-        int chunk = 0;
-        int clo = STD ? hi - 1 : lo;
-        int chi = STD ? hi : min(lo + qlen, hi);
-        float rmin = SF_INF; // per lane running minimum of the open chunk
-        int rpos = -1;
-        float s1 = SF_INF, s2 = SF_INF;
-        int bseg = -1, bchunk = 0, bpos = -1;
-        int ck = 0;
-
-        for (int b = 0; b < n_blocks; b++) {
-            // prefetch the next 64 reference events; published after the 32 macro-steps below
-            const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
-            const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
-            const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
-            const float2 *yb = ring + ((b & 1) ? 32 : 64) - lane;
-
-            if (fast)
-                sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
-            else
-                sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
-            __syncwarp();
-
-            // ---- last-row chunk minima (sigfish.c:891-901): this block produced the last row of columns
-            //      p0 .. p0+63; lane l looks at p0+2l and p0+2l+1 ----
-            {
-                const int p0 = SF_BLOCK_COLS * b - 2 * lq;
-                const int pos0 = p0 + 2 * lane;
-                float v0, v1;
-                if (fast) {
-                    const float2 v = *reinterpret_cast<const float2 *>(last + 2 * lane);
-                    v0 = v.x; v1 = v.y;
-                } else {
-                    const float2 v = *reinterpret_cast<const float2 *>(last + (lane * R + rq) * 2);
-                    v0 = v.x; v1 = v.y;
-                }
-                for (;;) {
-                    if (pos0 >= clo && pos0 < chi && v0 < rmin) {
-                        rmin = v0;
-                        rpos = pos0;
-                    }
-                    if (pos0 + 1 >= clo && pos0 + 1 < chi && v1 < rmin) {
-                        rmin = v1;
-                        rpos = pos0 + 1;
-                    }
-                    if (chi > p0 + SF_BLOCK_COLS)
-                        break;
-                    // chunk complete: first strict minimum = smallest value, then smallest column
-                    float m = rmin;
-                    int mp = rpos;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float om = __shfl_xor_sync(full, m, o);
-                        const int op = __shfl_xor_sync(full, mp, o);
-                        if (om < m || (om == m && (unsigned)op < (unsigned)mp)) {
-                            m = om;
-                            mp = op;
-                        }
-                    }
-                    // update_aln(): a later candidate with an equal score ranks better
-                    if (m <= s1) {
-                        s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
-                    } else if (m < s2) {
-                        s2 = m;
-                    }
-                    rmin = SF_INF;
-                    rpos = -1;
-                    clo = chi;
-                    chunk++;
-                    if (clo >= hi) {
-                        si++;
-                        chunk = 0;
-                        if (si < si_end) {
-                            seg = a.segs[si];
-                            lo = (int)(seg.off - grp.begin);
-                            hi = lo + seg.rlen;
-                            clo = STD ? hi - 1 : lo;
-                        } else {
-                            clo = 0x7fffffff;
-                            hi = 0x7fffffff;
-                        }
-                    }
-                    chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
-                }
-            }
-
-            // ---- checkpoint of the skewed wavefront (for the start-coordinate pass) ----
-            if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    c[r * 32 + lane] = L[r];
-                c[R * 32 + lane] = dprev;
-                c[(R + 1) * 32 + lane] = botA;
-                ck++;
-            }
-
-            // publish block b+1 of the reference events (overwrites block b-1)
-            {
-                const int slot = ((b + 1) & 1) * 32 + lane;
-                const float2 v = make_float2(yn0, yn1);
-                ring[slot] = v;
-                ring[slot + 64] = v;
-            }
-            __syncwarp();
-        }
-
-        if (lane == 0) {
-            out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
         }
     }
 }
@@ -391,25 +489,202 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 #define SF_PAIR_LAST 68
 __host__ __device__ inline int sf_pair_smem_floats_per_warp() { return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST; }
 
-template <int R, bool STD, int RQ>
+// One (pair of reads, piece) task.  `read` / `valid` are per half; RESUME as in sf_score_task.
+template <int R, bool STD, int RQ, bool RESUME>
+__device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int read, const bool valid, const int pidx,
+                                             const int lane, float2 *ring, float *last)
+{
+    constexpr int W = SF_PAIR_LANES;
+    const unsigned full = 0xffffffffu;
+    const int ll = lane & (W - 1);  // lane inside the read
+    const int half = lane / W;      // which read of the pair
+    const int qlen = a.q_full;
+    const int lq = (qlen - 1) / R;  // lane (inside the half) holding the last query row; its register is RQ
+    const bool is_lq = ll == lq;
+    const int nz = ll != 0;
+    const sf_piece pc = a.pieces[pidx];
+    const sf_group grp = a.groups[pc.gid];
+    sf_taskres *out = a.res + (size_t)read * a.n_pieces + pidx;
+    int pflags = pc.flags | ((pc.flags & 1) << 2); // see sf_score_task
+
+    const float *y = a.stream + grp.begin;
+    const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
+    const int b_end = (pflags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
+    const int b_first = RESUME ? pc.b0 : ((pflags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
+
+    float x[R], L[R];
+    const float *q = a.queries + (size_t)read * a.q_cap;
+    float botA = SF_INF, botB = SF_INF;
+    float dprev = (ll == 0 && !STD) ? 0.0f : SF_INF;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row = ll * R + r;
+        x[r] = row < qlen ? q[row] : 0.0f;
+        L[r] = SF_INF;
+    }
+    if (RESUME) {
+        const float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + pc.b0 / grp.ck_every - 1) * (size_t)a.ck_floats;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            L[r] = c[r * W + ll];
+        dprev = c[R * W + ll];
+        botA = c[(R + 1) * W + ll];
+        botB = L[R - 1];
+    }
+
+    __syncwarp();
+    {
+        const int c0 = SF_BLOCK_COLS * b_first + 2 * lane, c1 = c0 + 1;
+        float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
+        if (!RESUME && b_first > 0 && lane == 0)
+            v.x = SF_INF; // virtual column -1 of the warm-up window
+        float2 pv = make_float2(SF_INF, SF_INF);
+        if (RESUME)
+            pv = make_float2(c0 - SF_BLOCK_COLS < n_pos ? y[c0 - SF_BLOCK_COLS] : SF_INF,
+                             c1 - SF_BLOCK_COLS < n_pos ? y[c1 - SF_BLOCK_COLS] : SF_INF);
+        const int cur = (b_first & 1) * 32 + lane, prv = ((b_first & 1) ^ 1) * 32 + lane;
+        ring[cur] = v; ring[cur + 64] = v;
+        ring[prv] = pv; ring[prv + 64] = pv;
+    }
+    __syncwarp();
+
+    // chunk bookkeeping: shared by the two reads (same query length, same segments)
+    int si = grp.seg0;
+    const int si_end = grp.seg0 + grp.nseg;
+    sf_seg seg = a.segs[si];
+    int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
+    int chunk = 0;
+    int clo = STD ? hi - 1 : lo;
+    int ck = 0;
+    if (pflags & 3) {
+        if (pflags & 2)
+            hi = min(hi, SF_BLOCK_COLS * pc.b1 - 2 * lq);
+        if (pflags & 1) {
+            clo = SF_BLOCK_COLS * pc.b0 - 2 * lq;
+            chunk = (clo - lo) / qlen;
+            ck = pc.b0 / grp.ck_every;
+        }
+    }
+    int chi = STD ? hi : min(lo + (chunk + 1) * qlen, hi);
+    // per read: the lanes of a half track the last row of their own read
+    float rmin = SF_INF, s1 = SF_INF, s2 = SF_INF;
+    int rpos = -1, bseg = -1, bchunk = 0, bpos = -1;
+
+    for (int b = b_first; b < b_end; b++) {
+        const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
+        const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
+        const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
+        const float2 *yb = ring + ((b & 1) ? 32 : 64) - ll;
+
+        sf_dtw_block<R, STD, RQ, W>(x, L, botA, botB, dprev, yb, last + SF_PAIR_LAST * half, is_lq, nz);
+        __syncwarp();
+
+        // ---- last-row chunk minima: this block produced columns p0 .. p0+63 of both reads; lane ll of a
+        //      half looks at p0+4ll .. p0+4ll+3 of its own read ----
+        {
+            const int p0 = SF_BLOCK_COLS * b - 2 * lq;
+            const int pos0 = p0 + 4 * ll;
+            const float4 v = *reinterpret_cast<const float4 *>(last + SF_PAIR_LAST * half + 4 * ll);
+            for (;;) {
+                if (pos0 >= clo && pos0 < chi && v.x < rmin) { rmin = v.x; rpos = pos0; }
+                if (pos0 + 1 >= clo && pos0 + 1 < chi && v.y < rmin) { rmin = v.y; rpos = pos0 + 1; }
+                if (pos0 + 2 >= clo && pos0 + 2 < chi && v.z < rmin) { rmin = v.z; rpos = pos0 + 2; }
+                if (pos0 + 3 >= clo && pos0 + 3 < chi && v.w < rmin) { rmin = v.w; rpos = pos0 + 3; }
+                if (chi > p0 + SF_BLOCK_COLS)
+                    break;
+                float m = rmin;
+                int mp = rpos;
+#pragma unroll
+                for (int o = W / 2; o > 0; o >>= 1) { // stays inside the half
+                    const float om = __shfl_xor_sync(full, m, o);
+                    const int op = __shfl_xor_sync(full, mp, o);
+                    if (om < m || (om == m && (unsigned)op < (unsigned)mp)) {
+                        m = om;
+                        mp = op;
+                    }
+                }
+                if (pflags & 4) { // head edge of a piece
+                    if (ll == 0 && valid) { out->hmin = m; out->hpos = mp >= 0 ? mp - lo : -1; out->hchunk = chunk; }
+                    pflags &= ~4;
+                } else if ((pflags & 2) && chi >= hi) { // tail edge of a piece
+                    if (ll == 0 && valid) { out->tmin = m; out->tpos = mp >= 0 ? mp - lo : -1; out->tchunk = chunk; }
+                } else if (m <= s1) {
+                    s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
+                } else if (m < s2) {
+                    s2 = m;
+                }
+                rmin = SF_INF;
+                rpos = -1;
+                clo = chi;
+                chunk++;
+                if (clo >= hi) {
+                    si++;
+                    chunk = 0;
+                    if (si < si_end) {
+                        seg = a.segs[si];
+                        lo = (int)(seg.off - grp.begin);
+                        hi = lo + seg.rlen;
+                        clo = STD ? hi - 1 : lo;
+                    } else {
+                        clo = 0x7fffffff;
+                        hi = 0x7fffffff;
+                    }
+                }
+                chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
+            }
+        }
+
+        // ---- checkpoint (half-warp layout), one per read ----
+        if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
+            if (valid) {
+                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    c[r * W + ll] = L[r];
+                c[R * W + ll] = dprev;
+                c[(R + 1) * W + ll] = botA;
+            }
+            ck++;
+        }
+        // ---- warm front of a piece ----
+        if (!RESUME && (pflags & 1) && b + 1 == pc.b0 && valid) {
+            float *c = a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                c[r * W + ll] = L[r];
+            c[R * W + ll] = dprev;
+            c[(R + 1) * W + ll] = botA;
+        }
+
+        {
+            const int slot = ((b + 1) & 1) * 32 + lane;
+            const float2 v = make_float2(yn0, yn1);
+            ring[slot] = v;
+            ring[slot + 64] = v;
+        }
+        __syncwarp();
+    }
+
+    if (ll == 0 && valid) {
+        out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
+    }
+}
+
+template <int R, bool STD, int RQ, bool FIX = false>
 __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_pair_kernel(const sf_dtw_args a)
 {
     constexpr int W = SF_PAIR_LANES;
     extern __shared__ float2 sf_smem2[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int ll = lane & (W - 1);  // lane inside the read
-    const int half = lane / W;      // which read of the pair
+    const int half = lane / W;
     float2 *ring = sf_smem2 + warp * (sf_pair_smem_floats_per_warp() / 2);
     float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
     const int n_list = *a.n_list;
-    const int n_units = (n_list + 1) / 2;
-    const unsigned n_tasks = (unsigned)a.n_groups * (unsigned)n_units;
-    const int qlen = a.q_full;
-    const int lq = (qlen - 1) / R;  // lane (inside the half) holding the last query row; its register is RQ
-    const bool is_lq = ll == lq;
-    const int nz = ll != 0;
+    // FIX: one read per warp (both halves carry it, the upper one writes nothing)
+    const int n_units = FIX ? n_list : (n_list + 1) / 2;
+    const unsigned n_tasks = (unsigned)(FIX ? a.n_split : a.n_pieces) * (unsigned)n_units;
 
     for (;;) {
         unsigned task = 0;
@@ -420,140 +695,73 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_p
             break;
         const int gi = task / (unsigned)n_units;
         const int unit = task - gi * n_units;
-        const int gid = a.order[gi];
-        const sf_group grp = a.groups[gid];
-        const int idx = 2 * unit + half;
-        const bool valid = idx < n_list;           // an odd list: the second half repeats the first read
-        const int read = a.list[valid ? idx : 2 * unit];
-
-        float x[R], L[R];
-        const float *q = a.queries + (size_t)read * a.q_cap;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = ll * R + r;
-            x[r] = row < qlen ? q[row] : 0.0f;
-            L[r] = SF_INF;
-        }
-        float botA = SF_INF, botB = SF_INF;
-        float dprev = (ll == 0 && !STD) ? 0.0f : SF_INF;
-
-        const float *y = a.stream + grp.begin;
-        const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
-        const int n_blocks = ((n_pos - 1) / 2 + lq + 32) >> 5;
-
-        __syncwarp();
-        {
-            const int c0 = 2 * lane, c1 = c0 + 1;
-            const float2 v = make_float2(c0 < n_pos ? y[c0] : SF_INF, c1 < n_pos ? y[c1] : SF_INF);
-            ring[lane] = v; ring[64 + lane] = v;
-            const float2 inf2 = make_float2(SF_INF, SF_INF);
-            ring[32 + lane] = inf2; ring[96 + lane] = inf2;
-        }
-        __syncwarp();
-
-        // chunk bookkeeping: shared by the two reads (same query length, same segments)
-        int si = grp.seg0;
-        const int si_end = grp.seg0 + grp.nseg;
-        sf_seg seg = a.segs[si];
-        int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
-        int chunk = 0;
-        int clo = STD ? hi - 1 : lo;
-        int chi = STD ? hi : min(lo + qlen, hi);
-        // per read: the lanes of a half track the last row of their own read
-        float rmin = SF_INF, s1 = SF_INF, s2 = SF_INF;
-        int rpos = -1, bseg = -1, bchunk = 0, bpos = -1;
-        int ck = 0;
-
-        for (int b = 0; b < n_blocks; b++) {
-            const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
-            const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
-            const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
-            const float2 *yb = ring + ((b & 1) ? 32 : 64) - ll;
-
-            sf_dtw_block<R, STD, RQ, W>(x, L, botA, botB, dprev, yb, last + SF_PAIR_LAST * half, is_lq, nz);
-            __syncwarp();
-
-            // ---- last-row chunk minima: this block produced columns p0 .. p0+63 of both reads; lane ll of a
-            //      half looks at p0+4ll .. p0+4ll+3 of its own read ----
-            {
-                const int p0 = SF_BLOCK_COLS * b - 2 * lq;
-                const int pos0 = p0 + 4 * ll;
-                const float4 v = *reinterpret_cast<const float4 *>(last + SF_PAIR_LAST * half + 4 * ll);
-                for (;;) {
-                    if (pos0 >= clo && pos0 < chi && v.x < rmin) { rmin = v.x; rpos = pos0; }
-                    if (pos0 + 1 >= clo && pos0 + 1 < chi && v.y < rmin) { rmin = v.y; rpos = pos0 + 1; }
-                    if (pos0 + 2 >= clo && pos0 + 2 < chi && v.z < rmin) { rmin = v.z; rpos = pos0 + 2; }
-                    if (pos0 + 3 >= clo && pos0 + 3 < chi && v.w < rmin) { rmin = v.w; rpos = pos0 + 3; }
-                    if (chi > p0 + SF_BLOCK_COLS)
-                        break;
-                    float m = rmin;
-                    int mp = rpos;
-#pragma unroll
-                    for (int o = W / 2; o > 0; o >>= 1) { // stays inside the half
-                        const float om = __shfl_xor_sync(full, m, o);
-                        const int op = __shfl_xor_sync(full, mp, o);
-                        if (om < m || (om == m && (unsigned)op < (unsigned)mp)) {
-                            m = om;
-                            mp = op;
-                        }
-                    }
-                    if (m <= s1) {
-                        s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
-                    } else if (m < s2) {
-                        s2 = m;
-                    }
-                    rmin = SF_INF;
-                    rpos = -1;
-                    clo = chi;
-                    chunk++;
-                    if (clo >= hi) {
-                        si++;
-                        chunk = 0;
-                        if (si < si_end) {
-                            seg = a.segs[si];
-                            lo = (int)(seg.off - grp.begin);
-                            hi = lo + seg.rlen;
-                            clo = STD ? hi - 1 : lo;
-                        } else {
-                            clo = 0x7fffffff;
-                            hi = 0x7fffffff;
-                        }
-                    }
-                    chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
-                }
+        if (!FIX) {
+            const int idx = 2 * unit + half;
+            const bool valid = idx < n_list;           // an odd list: the second half repeats the first read
+            const int read = a.list[valid ? idx : 2 * unit];
+            sf_pair_task<R, STD, RQ, false>(a, read, valid, a.order[gi], lane, ring, last);
+        } else {
+            const int read = a.list[unit];
+            const int k0 = a.first_bad[(size_t)read * a.n_split + gi];
+            if (k0 == 0x7fffffff)
+                continue;
+            const int p0 = a.split_first[gi], K = a.split_count[gi];
+#pragma unroll 1
+            for (int k = k0; k < K; k++) {
+                if (k > k0 && sf_fronts_equal(a, read, p0 + k, lane, (R + 2) * W))
+                    continue;
+                sf_pair_task<R, STD, RQ, true>(a, read, half == 0, p0 + k, lane, ring, last);
+                __syncwarp();
             }
-
-            // ---- checkpoint (half-warp layout), one per read ----
-            if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-                if (valid) {
-                    float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
-#pragma unroll
-                    for (int r = 0; r < R; r++)
-                        c[r * W + ll] = L[r];
-                    c[R * W + ll] = dprev;
-                    c[(R + 1) * W + ll] = botA;
-                }
-                ck++;
-            }
-
-            {
-                const int slot = ((b + 1) & 1) * 32 + lane;
-                const float2 v = make_float2(yn0, yn1);
-                ring[slot] = v;
-                ring[slot + 64] = v;
-            }
-            __syncwarp();
-        }
-
-        if (ll == 0 && valid) {
-            sf_taskres *out = a.res + (size_t)read * a.n_groups + gid;
-            out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
         }
     }
     // This grid was released early by sf_dtw_score_kernel (griddepcontrol.launch_dependents).  The kernels behind it
     // in the stream read the results of BOTH; they are ordered behind this grid only, so this grid must not
     // complete before its prerequisite has completed and flushed: wait for it here, after the work.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!FIX)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Marks, for every (read, split group), the first piece whose warm front differs from the checkpoint its predecessor
+// wrote at the same boundary (atomicMin into first_bad, preset to 0x7fffffff).  One warp per (read, warm front).
+struct sf_verify_args {
+    const sf_piece *pieces;
+    const sf_group *groups;
+    const int32_t *warm_piece;  // [n_warm] piece id of warm front w
+    const sf_readinfo *info;
+    const float *warm, *ckpt;
+    int32_t n_reads, n_warm, n_split, ck_floats;
+    int64_t ck_per_read;
+    int32_t n_f, n_f_pair;      // floats of the warp-per-read layout / of the pair layout (reads with status bit 5)
+    int32_t *first_bad;
+    int32_t *n_bad;             // statistics: fronts that differed in this batch
+};
+
+__global__ void sf_verify_kernel(const sf_verify_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_items = (long long)a.n_reads * a.n_warm;
+    for (long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items;
+         item += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int read = (int)(item / a.n_warm);
+        const int w = (int)(item - (long long)read * a.n_warm);
+        const sf_readinfo ri = a.info[read];
+        if (ri.qlen <= 0)
+            continue;
+        const sf_piece pc = a.pieces[a.warm_piece[w]];
+        const sf_group grp = a.groups[pc.gid];
+        const unsigned *x = reinterpret_cast<const unsigned *>(a.warm + ((size_t)read * a.n_warm + w) * (size_t)a.ck_floats);
+        const unsigned *f = reinterpret_cast<const unsigned *>(
+            a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + pc.b0 / grp.ck_every - 1) * (size_t)a.ck_floats);
+        const int n_f = (ri.status & 32) ? a.n_f_pair : a.n_f;
+        bool ne = false;
+        for (int i = lane; i < n_f; i += 32)
+            ne |= x[i] != f[i];
+        if (__any_sync(0xffffffffu, ne) && lane == 0) {
+            atomicMin(a.first_bad + (size_t)read * a.n_split + pc.sidx, pc.k);
+            atomicAdd(a.n_bad, 1);
+        }
+    }
 }
 
 // Splits the reads of a batch into those with exactly q_full events (pair kernel; flagged with status bit 5)

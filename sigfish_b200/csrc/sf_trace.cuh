@@ -27,11 +27,13 @@ struct sf_trace_args {
     const sf_group *groups;
     const int32_t *seg_group; // segment -> group id
     int32_t n_groups;
+    const sf_piece *pieces;   // the DTW tasks of one read (split level of the batch)
+    int32_t n_pieces;
     int32_t n_reads;
     const float *queries;
     const sf_readinfo *info;
     int32_t q_cap;
-    const sf_taskres *res;
+    const sf_taskres *res;    // [n_reads][n_pieces]
     const float *ckpt;
     int64_t ck_per_read;
     int32_t ck_floats;        // floats per checkpoint
@@ -77,6 +79,33 @@ __device__ __forceinline__ void sf_top_merge(sf_top &a, const sf_top &b)
         a.s2 = fminf(second, a.s2);
     } else {
         a.s2 = fminf(a.s2, fminf(b.seg >= 0 ? b.s1 : SF_INF, b.s2));
+    }
+}
+
+// Merges the results of task t of a read into `top`: the candidates of the chunks lying wholly inside the task,
+// and -- for a piece with a successor -- the chunk cut by the boundary between the two: its minimum is the smaller
+// of the two parts, at equal values the earlier column, i.e. the part in this piece (first strict minimum,
+// sigfish.c:891-901).  When the boundary happens to fall between two chunks the two parts are candidates of their own.
+__device__ __forceinline__ void sf_merge_task(sf_top &top, const sf_trace_args &a, const sf_taskres *res, const int t)
+{
+    const sf_taskres tr = res[t];
+    sf_top b; b.s1 = tr.s1; b.s2 = tr.s2; b.seg = tr.seg; b.chunk = tr.chunk; b.pos = tr.pos;
+    sf_top_merge(top, b);
+    const sf_piece pc = a.pieces[t];
+    if (pc.flags & 2) {
+        const sf_taskres nx = res[t + 1]; // the next piece of the same segment
+        const int seg = a.groups[pc.gid].seg0;
+        sf_top e; e.s2 = SF_INF; e.seg = seg;
+        if (tr.tchunk == nx.hchunk) {
+            const bool first = tr.tmin <= nx.hmin;
+            e.s1 = first ? tr.tmin : nx.hmin; e.chunk = tr.tchunk; e.pos = first ? tr.tpos : nx.hpos;
+            sf_top_merge(top, e);
+        } else {
+            e.s1 = tr.tmin; e.chunk = tr.tchunk; e.pos = tr.tpos;
+            sf_top_merge(top, e);
+            e.s1 = nx.hmin; e.chunk = nx.hchunk; e.pos = nx.hpos;
+            sf_top_merge(top, e);
+        }
     }
 }
 
@@ -435,11 +464,8 @@ __global__ void __launch_bounds__(128, sf_trace_min_blocks(R, R2)) sf_trace_kern
     // ---- merge the per-group results of this read ----
     sf_top top;
     top.s1 = SF_INF; top.s2 = SF_INF; top.seg = -1; top.chunk = 0; top.pos = -1;
-    for (int g = lane; g < a.n_groups; g += 32) {
-        const sf_taskres tr = a.res[(size_t)read * a.n_groups + g];
-        sf_top b; b.s1 = tr.s1; b.s2 = tr.s2; b.seg = tr.seg; b.chunk = tr.chunk; b.pos = tr.pos;
-        sf_top_merge(top, b);
-    }
+    for (int t = lane; t < a.n_pieces; t += 32)
+        sf_merge_task(top, a, a.res + (size_t)read * a.n_pieces, t);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sf_top b;
@@ -492,11 +518,8 @@ __global__ void __launch_bounds__(128, sf_trace_min_blocks(R, 0)) sf_trace_pair_
     // ---- merge the per-group results, 16 lanes per read ----
     sf_top top;
     top.s1 = SF_INF; top.s2 = SF_INF; top.seg = -1; top.chunk = 0; top.pos = -1;
-    for (int g = ll; g < a.n_groups; g += 16) {
-        const sf_taskres tr = a.res[(size_t)read * a.n_groups + g];
-        sf_top b; b.s1 = tr.s1; b.s2 = tr.s2; b.seg = tr.seg; b.chunk = tr.chunk; b.pos = tr.pos;
-        sf_top_merge(top, b);
-    }
+    for (int t = ll; t < a.n_pieces; t += 16)
+        sf_merge_task(top, a, a.res + (size_t)read * a.n_pieces, t);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
         sf_top b;

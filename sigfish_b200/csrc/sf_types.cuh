@@ -40,14 +40,37 @@ struct sf_group {
     int64_t ck_prefix;  // checkpoints of earlier groups (per read)
 };
 
-// what one (read, group) task reports
+// A DTW task: a whole group, or -- for a group that is one long segment -- a *piece* of it: blocks [b0, b1) of the
+// group's block grid (64 columns per block; position 0 = the group's sentinel).  A piece with a predecessor starts
+// `warm_blocks` blocks early behind a virtual +INF column, and its wavefront at the piece boundary (the "warm
+// front") is compared bit for bit with the front its predecessor reached there (a regular checkpoint: piece
+// boundaries are multiples of ck_every).  Equal fronts => everything the piece computes from the boundary on is
+// the full-matrix recurrence; a piece whose fronts differ is redone from the predecessor's front (sf_verify_kernel,
+// FIX instantiations of the DTW kernels).
+struct sf_piece {
+    int32_t gid;     // group
+    int32_t b0, b1;  // own blocks; b1 is ignored for the last piece (it runs to the end of the group)
+    int32_t flags;   // bit 0: has a predecessor (warm-up, head edge); bit 1: has a successor (tail edge)
+    int32_t widx;    // index of its warm front among the read's warm fronts (flags & 1)
+    int32_t sidx;    // index of its group among the split groups (flags != 0)
+    int32_t k;       // piece number inside the group
+    int32_t pad;
+};
+
+// what one (read, piece) task reports
 struct sf_taskres {
     float s1;        // best candidate score
     float s2;        // second best candidate score (value only)
     int32_t seg;     // global segment index of the best candidate
     int32_t chunk;   // chunk index inside the segment (tie order)
     int32_t pos;     // end column inside the segment (-1: no finite cell)
-    int32_t pad[3];
+    // pieces only: the chunks cut by the piece's two ends are reported apart and joined with the neighbour's part
+    // by the merge (first strict minimum over both parts, sigfish.c:891-901)
+    float hmin;      // head edge: minimum of the part of chunk `hchunk` inside this piece
+    int32_t hpos, hchunk;
+    float tmin;      // tail edge
+    int32_t tpos, tchunk;
+    int32_t pad;
 };
 
 // per-read record produced by the event kernel and consumed by DTW + host epilogue

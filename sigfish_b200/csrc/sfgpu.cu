@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +31,21 @@
 namespace {
 
 thread_local char g_err[512] = "";
+
+// SFGPU_TRACE=1 in the environment: wall-clock stamps of the set-up steps on stderr (where start-up time goes)
+struct sf_tracer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    sf_tracer() : on(getenv("SFGPU_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void operator()(int dev, const char *what) const
+    {
+        if (!on)
+            return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[sfgpu::%.1f ms] gpu %d: %s\n", ms, dev, what);
+    }
+};
+const sf_tracer g_trace;
 
 struct sf_slot {
     cudaStream_t stream = nullptr;
@@ -59,8 +75,14 @@ struct sf_slot {
     sf_taskres *d_res = nullptr;
     float *d_ckpt = nullptr;
     sf_hit *d_hits = nullptr;
-    unsigned int *d_counter = nullptr;  // [2] task queues of the two DTW kernels
-    int32_t *d_list_full = nullptr, *d_list_other = nullptr, *d_counts = nullptr; // sf_partition_kernel
+    unsigned int *d_counter = nullptr;  // [4] task queues of the two DTW kernels and of their redo passes
+    int32_t *d_list_full = nullptr, *d_list_other = nullptr, *d_counts = nullptr; // sf_partition_kernel; [2] = fronts that differed
+    int32_t *h_counts = nullptr;        // pinned copy of d_counts
+    // pieces of split segments: warm fronts, first differing piece per (read, split group); sized per batch
+    float *d_warm = nullptr;
+    int32_t *d_first_bad = nullptr;
+    size_t cap_res = 0, cap_warm = 0, cap_bad = 0;
+    int level = 0;                      // split level of the batch in flight
     // state
     int32_t n_reads = 0;
     int64_t n_samples = 0; // padded
@@ -70,6 +92,20 @@ struct sf_slot {
 };
 
 } // namespace
+
+// One way of cutting the groups into DTW tasks: `len` blocks per piece of a long single-segment group (0: every
+// group is one task).  Several levels are prepared with the reference; each batch picks the one with the smallest
+// expected time for its number of reads (run_stages).
+struct sf_level {
+    int32_t len = 0;
+    std::vector<sf_piece> pieces;
+    std::vector<int32_t> order, warm_piece, split_first, split_count;
+    int32_t n_pieces = 0, n_warm = 0, n_split = 0;
+    double blocks_per_read = 0.0; // executed blocks of one read: own blocks + warm-up + pipeline fill
+    double longest = 0.0;         // blocks of the longest task
+    sf_piece *d_pieces = nullptr;
+    int32_t *d_order = nullptr, *d_warm_piece = nullptr, *d_split_first = nullptr, *d_split_count = nullptr;
+};
 
 struct sfgpu_ctx {
     sfgpu_opt_t opt;
@@ -94,6 +130,9 @@ struct sfgpu_ctx {
     int64_t ck_per_read = 0, ref_columns = 0;
     int32_t min_window = 0;
     int32_t ck_min_cols = 2048; // segments longer than this get wavefront checkpoints (reserved[0] overrides)
+    std::vector<sf_level> levels; // levels[0]: no splitting
+    int32_t warm_blocks = 0;      // warm-up of a piece, in blocks of 64 columns
+    int32_t force_level_len = 0;  // test knob (reserved[4]): > 0 piece length in checkpoint periods, < 0 never split
     std::vector<sf_slot> slots;
     int dtw_blocks_per_sm = 0;
     char err[512];
@@ -150,13 +189,17 @@ void slot_free_buffers(sf_slot &s)
     dfree(s.d_signal); dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean);
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
     dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
-    dfree(s.d_list_full); dfree(s.d_list_other);
+    dfree(s.d_list_full); dfree(s.d_list_other); dfree(s.d_warm); dfree(s.d_first_bad);
     s.cap_reads = 0;
     s.cap_samples = 0;
+    s.cap_res = s.cap_warm = s.cap_bad = 0;
 }
 
 int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
 {
+    const bool grow = n_samples > s.cap_samples || n_reads > s.cap_reads;
+    if (grow)
+        g_trace(c->opt.device, "slot_reserve: growing buffers");
     if (n_samples > s.cap_samples) {
         const int64_t cap = std::max<int64_t>(n_samples + n_samples / 4, 1 << 20);
         hfree(s.h_signal);
@@ -170,7 +213,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         const int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
-        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
+        dfree(s.d_queries); dfree(s.d_info); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
         dfree(s.d_list_full); dfree(s.d_list_other);
         s.cap_reads = 0;
         const size_t n = (size_t)cap;
@@ -185,7 +228,6 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         SF_CUDA(c, cudaMalloc(&s.d_ev_len, sizeof(float) * n * c->ev_cap));
         SF_CUDA(c, cudaMalloc(&s.d_queries, sizeof(float) * n * c->q_cap));
         SF_CUDA(c, cudaMalloc(&s.d_info, sizeof(sf_readinfo) * n));
-        SF_CUDA(c, cudaMalloc(&s.d_res, sizeof(sf_taskres) * n * std::max(1, c->n_groups)));
         if (c->ck_per_read > 0)
             SF_CUDA(c, cudaMalloc(&s.d_ckpt, sizeof(float) * n * c->ck_per_read * (size_t)c->ck_floats));
         SF_CUDA(c, cudaMalloc(&s.d_hits, sizeof(sf_hit) * n));
@@ -198,6 +240,8 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         }
         s.cap_reads = cap;
     }
+    if (grow)
+        g_trace(c->opt.device, "slot_reserve: done");
     return SFGPU_OK;
 }
 
@@ -206,7 +250,7 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
 template <int R, bool STD> int dtw_occupancy(size_t smem)
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_score_kernel<R, STD>, SF_DTW_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_score_kernel<R, STD, false>, SF_DTW_THREADS, smem);
     return nb;
 }
 
@@ -217,10 +261,30 @@ cudaError_t launch_dtw(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
+// redo pass of the warp-per-read kernel (pieces whose warm front did not verify); subsequence DTW only
+template <int R, bool STD>
+cudaError_t launch_dtw_fix(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
+{
+    if constexpr (!STD) {
+        sf_dtw_score_kernel<R, false, true><<<grid, SF_DTW_THREADS, smem, st>>>(a);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int RQ, bool STD> cudaError_t launch_pair_fix(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
+{
+    if constexpr (!STD) {
+        sf_dtw_pair_kernel<16, false, RQ, true><<<grid, SF_DTW_THREADS, smem, st>>>(a);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int RQ, bool STD> int pair_occupancy(size_t smem)
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_pair_kernel<16, STD, RQ>, SF_DTW_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_pair_kernel<16, STD, RQ, false>, SF_DTW_THREADS, smem);
     return nb;
 }
 
@@ -237,7 +301,7 @@ template <int RQ, bool STD> cudaError_t launch_pair(const sf_dtw_args &a, int gr
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, sf_dtw_pair_kernel<16, STD, RQ>, a);
+    return cudaLaunchKernelEx(&cfg, sf_dtw_pair_kernel<16, STD, RQ, false>, a);
 }
 
 // the pair kernel is instantiated for the query sizes 250 (last row in register 9 of its lane) and 256 (15)
@@ -296,6 +360,9 @@ template <typename F, int... Rs> bool dispatch_rows(int rows, bool std_dtw, F &&
         constexpr bool STD = decltype(std_tag_)::value;                                           \
         EXPR;                                                                                     \
     }, sf_rows{})
+
+int pick_level(const sfgpu_ctx *c, int n);
+int slot_reserve_level(sfgpu_ctx *c, sf_slot &s, int n, const sf_level &lv);
 
 // the device stages of one batch, on the slot's stream
 int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
@@ -361,13 +428,22 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
     }
     SF_CUDA(c, cudaEventRecord(s.ev[2], st));
     if (n > 0) {
-        SF_CUDA(c, cudaMemsetAsync(s.d_counter, 0, sizeof(unsigned int) * 2, st));
+        s.level = pick_level(c, n);
+        const sf_level &lv = c->levels[s.level];
+        int rcl = slot_reserve_level(c, s, n, lv);
+        if (rcl)
+            return rcl;
+        SF_CUDA(c, cudaMemsetAsync(s.d_counter, 0, sizeof(unsigned int) * 4, st));
+        SF_CUDA(c, cudaMemsetAsync(s.d_counts + 2, 0, sizeof(int32_t), st));
+        if (lv.n_split > 0)
+            SF_CUDA(c, cudaMemsetAsync(s.d_first_bad, 0x7f, sizeof(int32_t) * (size_t)n * lv.n_split, st));
         sf_dtw_args da;
         da.stream = c->d_stream;
         da.segs = c->d_segs;
         da.groups = c->d_groups;
-        da.order = c->d_order;
-        da.n_groups = c->n_groups;
+        da.pieces = lv.d_pieces;
+        da.order = lv.d_order;
+        da.n_pieces = lv.n_pieces;
         da.n_reads = n;
         da.queries = s.d_queries;
         da.info = s.d_info;
@@ -380,41 +456,90 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         da.list = nullptr;
         da.n_list = nullptr;
         da.q_full = c->opt.query_size;
+        da.warm = s.d_warm;
+        da.n_warm = lv.n_warm;
+        da.warm_blocks = c->warm_blocks;
+        da.first_bad = s.d_first_bad;
+        da.n_split = lv.n_split;
+        da.split_first = lv.d_split_first;
+        da.split_count = lv.d_split_count;
         const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(c->R);
-        const long long n_tasks = (long long)n * c->n_groups;
+        const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
+        const long long n_tasks = (long long)n * lv.n_pieces;
+        if (n_tasks > 0x7ffffff0ll)
+            return fail(c, SFGPU_ELIMIT, "batch of %d reads x %d tasks per read exceeds the task counter; use a smaller batch", n, lv.n_pieces);
         const long long want = (n_tasks + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * c->dtw_blocks_per_sm));
+        const long long pwant = ((n_tasks + 1) / 2 + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
+        const int pgrid = c->R2 > 0 ? (int)std::max<long long>(1, std::min<long long>(pwant, (long long)c->sm_count * c->pair_blocks_per_sm)) : 0;
         cudaError_t e = cudaErrorInvalidValue;
+        sf_dtw_args oa = da, pa = da;
         if (c->R2 > 0) {
             // Reads with exactly q events run two per warp (pair kernel), the others one per warp.  The two
             // persistent kernels share the GPU: the warp-per-read kernel is launched first and releases its
             // dependents as soon as its blocks are resident (griddepcontrol.launch_dependents); the pair kernel
             // is launched with programmatic stream serialisation, so it starts then instead of after the end.
             // Blocks of the first kernel that find the queue empty exit at once and leave their place to pair
-            // blocks: a few ragged reads in a batch cost no extra wave (a task on a 1 Mb contig runs ~0.2 s).
+            // blocks: a few ragged reads in a batch cost no extra wave.
             sf_partition_kernel<<<1, 32, 0, st>>>(s.d_info, n, c->opt.query_size, s.d_list_full, s.d_list_other, s.d_counts);
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
-            sf_dtw_args oa = da;
             oa.list = s.d_list_other;
             oa.n_list = s.d_counts + 1;
             oa.counter = s.d_counter + 1;
             SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(oa, grid, smem, st)));
             SF_CUDA(c, e);
             s.timing.dtw_launches++;
-            da.list = s.d_list_full;
-            da.n_list = s.d_counts;
-            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
-            const long long pwant = ((n_tasks + 1) / 2 + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
-            const int pgrid = (int)std::max<long long>(1, std::min<long long>(pwant, (long long)c->sm_count * c->pair_blocks_per_sm));
+            pa.list = s.d_list_full;
+            pa.n_list = s.d_counts;
             e = cudaErrorInvalidValue;
-            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(da, pgrid, psmem, st)));
+            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(pa, pgrid, psmem, st)));
             SF_CUDA(c, e);
         } else {
-            SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(da, grid, smem, st)));
+            SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(oa, grid, smem, st)));
             SF_CUDA(c, e);
         }
         s.timing.dtw_launches++;
+        if (lv.n_split > 0) {
+            // pieces of split segments: compare every warm front with the checkpoint its predecessor left at the
+            // same boundary, then redo what differs (normally nothing: the redo kernels find no flagged item)
+            sf_verify_args va;
+            va.pieces = lv.d_pieces;
+            va.groups = c->d_groups;
+            va.warm_piece = lv.d_warm_piece;
+            va.info = s.d_info;
+            va.warm = s.d_warm;
+            va.ckpt = s.d_ckpt;
+            va.n_reads = n;
+            va.n_warm = lv.n_warm;
+            va.n_split = lv.n_split;
+            va.ck_floats = c->ck_floats;
+            va.ck_per_read = c->ck_per_read;
+            va.n_f = sf_ckpt_floats(c->R);
+            va.n_f_pair = c->R2 > 0 ? (c->R2 + 2) * SF_PAIR_LANES : va.n_f;
+            va.first_bad = s.d_first_bad;
+            va.n_bad = s.d_counts + 2;
+            const long long items = (long long)n * lv.n_warm;
+            const int vgrid = (int)std::max<long long>(1, std::min<long long>((items + 7) / 8, (long long)c->sm_count * 8));
+            sf_verify_kernel<<<vgrid, 256, 0, st>>>(va);
+            SF_CUDA(c, cudaGetLastError());
+            s.timing.other_launches++;
+            const long long fwant = ((long long)n * lv.n_split + SF_DTW_WARPS - 1) / SF_DTW_WARPS;
+            oa.counter = s.d_counter + 2;
+            pa.counter = s.d_counter + 3;
+            e = cudaErrorInvalidValue;
+            SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw_fix<R, STD>(
+                oa, (int)std::max<long long>(1, std::min<long long>(fwant, (long long)c->sm_count * c->dtw_blocks_per_sm)), smem, st)));
+            SF_CUDA(c, e);
+            s.timing.dtw_launches++;
+            if (c->R2 > 0) {
+                e = cudaErrorInvalidValue;
+                SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair_fix<RQ, STD>(
+                    pa, (int)std::max<long long>(1, std::min<long long>(fwant, (long long)c->sm_count * c->pair_blocks_per_sm)), psmem, st)));
+                SF_CUDA(c, e);
+                s.timing.dtw_launches++;
+            }
+        }
     }
     SF_CUDA(c, cudaEventRecord(s.ev[3], st));
     if (n > 0) {
@@ -424,6 +549,8 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ta.groups = c->d_groups;
         ta.seg_group = c->d_seg_group;
         ta.n_groups = c->n_groups;
+        ta.pieces = c->levels[s.level].d_pieces;
+        ta.n_pieces = c->levels[s.level].n_pieces;
         ta.n_reads = n;
         ta.queries = s.d_queries;
         ta.info = s.d_info;
@@ -445,6 +572,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
     if (n > 0) {
         SF_CUDA(c, cudaMemcpyAsync(s.h_info, s.d_info, sizeof(sf_readinfo) * n, cudaMemcpyDeviceToHost, st));
         SF_CUDA(c, cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(sf_hit) * n, cudaMemcpyDeviceToHost, st));
+        SF_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, st));
     }
     SF_CUDA(c, cudaEventRecord(s.ev[5], st));
     s.busy = true;
@@ -475,6 +603,9 @@ int slot_wait(sfgpu_ctx *c, sf_slot &s)
             cells += (double)s.h_info[i].qlen * (double)c->ref_columns;
         s.timing.cells = cells;
         s.timing.samples = s.raw_samples;
+        s.timing.tasks_per_read = s.n_reads > 0 ? c->levels[s.level].n_pieces : 0;
+        s.timing.piece_blocks = s.n_reads > 0 ? c->levels[s.level].len : 0;
+        s.timing.redone_pieces = s.n_reads > 0 ? s.h_counts[2] : 0;
         s.timed = true;
     }
     return SFGPU_OK;
@@ -483,7 +614,76 @@ int slot_wait(sfgpu_ctx *c, sf_slot &s)
 void free_ref(sfgpu_ctx *c)
 {
     dfree(c->d_stream); dfree(c->d_segs); dfree(c->d_groups); dfree(c->d_order); dfree(c->d_seg_group);
+    for (auto &lv : c->levels) {
+        dfree(lv.d_pieces); dfree(lv.d_order); dfree(lv.d_warm_piece); dfree(lv.d_split_first); dfree(lv.d_split_count);
+    }
+    c->levels.clear();
     c->have_ref = false;
+}
+
+// Cuts the groups into tasks with pieces of `len` blocks (a multiple of every split group's checkpoint period, so
+// that the front at a piece's end is one of the regular checkpoints).  len == 0: no splitting.
+int build_level(sfgpu_ctx *c, int32_t len, sf_level &lv)
+{
+    lv = sf_level();
+    lv.len = len;
+    const bool std_dtw = (c->opt.flags & SFGPU_DTW) != 0;
+    const double fill = 1.5; // blocks a task spends filling / draining the lane pipeline
+    for (int g = 0; g < c->n_groups; g++) {
+        const sf_group &grp = c->groups[g];
+        const int64_t n_pos = grp.end - grp.begin;
+        // blocks whose end still lies inside the group, in checkpoint periods
+        const int64_t units = grp.ck_every > 0 ? (n_pos - 1) / ((int64_t)SF_BLOCK_COLS * grp.ck_every) : 0;
+        int64_t n_pc = 1;
+        if (len > 0 && !std_dtw && grp.nseg == 1 && grp.ck_every > 0 && len % grp.ck_every == 0)
+            n_pc = std::max<int64_t>(1, std::min<int64_t>(units, (n_pos / SF_BLOCK_COLS + len / 2) / len));
+        const int per = len > 0 && grp.ck_every > 0 ? len / grp.ck_every : 0;
+        if (n_pc > 1) {
+            lv.split_first.push_back((int32_t)lv.pieces.size());
+            lv.split_count.push_back((int32_t)n_pc);
+        }
+        (void)per;
+        for (int64_t k = 0; k < n_pc; k++) {
+            sf_piece pc;
+            pc.gid = g;
+            pc.k = (int32_t)k;
+            pc.pad = 0;
+            pc.flags = n_pc > 1 ? ((k > 0 ? 1 : 0) | (k + 1 < n_pc ? 2 : 0)) : 0;
+            // boundaries: the `units` checkpoint periods spread evenly over the pieces
+            pc.b0 = n_pc > 1 ? (int32_t)(k * units / n_pc) * grp.ck_every : 0;
+            pc.b1 = n_pc > 1 && k + 1 < n_pc ? (int32_t)((k + 1) * units / n_pc) * grp.ck_every : (int32_t)((n_pos + SF_BLOCK_COLS - 1) / SF_BLOCK_COLS);
+            pc.sidx = n_pc > 1 ? (int32_t)lv.split_first.size() - 1 : -1;
+            pc.widx = -1;
+            if (pc.flags & 1) {
+                pc.widx = lv.n_warm++;
+                lv.warm_piece.push_back((int32_t)lv.pieces.size());
+            }
+            const double own = pc.b1 - pc.b0, blocks = own + fill + ((pc.flags & 1) ? std::min(c->warm_blocks, pc.b0) : 0);
+            lv.blocks_per_read += blocks;
+            lv.longest = std::max(lv.longest, blocks);
+            lv.pieces.push_back(pc);
+        }
+    }
+    lv.n_pieces = (int32_t)lv.pieces.size();
+    lv.n_split = (int32_t)lv.split_first.size();
+    lv.order.resize(lv.n_pieces);
+    for (int i = 0; i < lv.n_pieces; i++)
+        lv.order[i] = i;
+    std::stable_sort(lv.order.begin(), lv.order.end(), [&](int a, int b) {
+        return (lv.pieces[a].b1 - lv.pieces[a].b0) > (lv.pieces[b].b1 - lv.pieces[b].b0);
+    });
+    auto up = [&](auto *&dst, const auto &v) -> int {
+        using T = std::remove_reference_t<decltype(*dst)>;
+        SF_CUDA(c, cudaMalloc(&dst, sizeof(T) * std::max<size_t>(1, v.size())));
+        if (!v.empty())
+            SF_CUDA(c, cudaMemcpy(dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+        return SFGPU_OK;
+    };
+    int rc;
+    if ((rc = up(lv.d_pieces, lv.pieces)) || (rc = up(lv.d_order, lv.order)) || (rc = up(lv.d_warm_piece, lv.warm_piece)) ||
+        (rc = up(lv.d_split_first, lv.split_first)) || (rc = up(lv.d_split_count, lv.split_count)))
+        return rc;
+    return SFGPU_OK;
 }
 
 // waits for all slots, releases their buffers (group count / checkpoint layout may change) and the
@@ -592,7 +792,96 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
     SF_CUDA(c, cudaMemcpy(c->d_seg_group, c->seg_group.data(), sizeof(int32_t) * c->n_seg, cudaMemcpyHostToDevice));
     sf_fill_inf_kernel<<<c->sm_count * 4, 256>>>(c->d_stream, (size_t)c->stream_len);
     SF_CUDA(c, cudaGetLastError());
+
+    // ---- task levels: level 0 = one task per group; further levels cut the long single-segment groups into
+    //      pieces of len = base * 2^j blocks, base = the smallest multiple of the checkpoint period that is at
+    //      least four warm-ups (and two chunks) long ----
+    c->levels.clear();
+    c->levels.emplace_back();
+    int rc0 = build_level(c, 0, c->levels.back());
+    if (rc0)
+        return rc0;
+    int32_t ck_e = 0;
+    int64_t longest_blocks = 0;
+    for (const auto &g : c->groups)
+        if (g.nseg == 1 && g.ck_every > 0) {
+            if (ck_e == 0) ck_e = g.ck_every; // every group with checkpoints has the same period
+            longest_blocks = std::max<int64_t>(longest_blocks, (g.end - g.begin) / SF_BLOCK_COLS);
+        }
+    if (ck_e > 0 && !(c->opt.flags & SFGPU_DTW) && c->force_level_len >= 0) {
+        // a piece must hold more than two chunks, so that the chunks cut by its two ends are different ones
+        const int32_t two_chunks = (2 * c->q_cap + SF_BLOCK_COLS - 1) / SF_BLOCK_COLS + 1;
+        const int32_t min_len = std::max(4 * c->warm_blocks, two_chunks);
+        int32_t base = ((min_len + ck_e - 1) / ck_e) * ck_e;
+        if (c->force_level_len > 0)
+            base = std::max(c->force_level_len, (two_chunks + ck_e - 1) / ck_e) * ck_e;
+        for (int64_t len = base; 2 * len <= longest_blocks + len / 2 && c->levels.size() < 24; len *= 2) {
+            c->levels.emplace_back();
+            rc0 = build_level(c, (int32_t)len, c->levels.back());
+            if (rc0)
+                return rc0;
+            if (c->levels.back().n_split == 0) {
+                sf_level &lv = c->levels.back();
+                dfree(lv.d_pieces); dfree(lv.d_order); dfree(lv.d_warm_piece); dfree(lv.d_split_first); dfree(lv.d_split_count);
+                c->levels.pop_back();
+                break;
+            }
+            if (c->force_level_len > 0)
+                break;
+        }
+    }
     SF_CUDA(c, cudaDeviceSynchronize());
+    return SFGPU_OK;
+}
+
+// the level with the smallest expected DTW time for a batch of n reads: work / task slots + half the longest task
+// (the expected idle tail of a persistent grid whose last tasks have that length)
+int pick_level(const sfgpu_ctx *c, int n)
+{
+    if (c->force_level_len > 0 && c->levels.size() > 1)
+        return 1;
+    const double slots = c->R2 > 0 ? (double)c->sm_count * c->pair_blocks_per_sm * SF_DTW_WARPS * 2
+                                   : (double)c->sm_count * c->dtw_blocks_per_sm * SF_DTW_WARPS;
+    int best = 0;
+    double best_t = 0.0;
+    for (size_t i = 0; i < c->levels.size(); i++) {
+        const sf_level &lv = c->levels[i];
+        const double t = std::max(lv.longest, (double)n * lv.blocks_per_read / slots + 0.5 * lv.longest);
+        if (i == 0 || t < best_t) {
+            best = (int)i;
+            best_t = t;
+        }
+    }
+    return best;
+}
+
+// per-batch buffers whose size depends on the split level
+int slot_reserve_level(sfgpu_ctx *c, sf_slot &s, int n, const sf_level &lv)
+{
+    const size_t need_res = (size_t)n * lv.n_pieces;
+    if (need_res > s.cap_res) {
+        dfree(s.d_res);
+        s.cap_res = 0;
+        const size_t cap = need_res + need_res / 4;
+        SF_CUDA(c, cudaMalloc(&s.d_res, sizeof(sf_taskres) * cap));
+        s.cap_res = cap;
+    }
+    const size_t need_warm = (size_t)n * lv.n_warm * (size_t)c->ck_floats;
+    if (need_warm > s.cap_warm) {
+        dfree(s.d_warm);
+        s.cap_warm = 0;
+        const size_t cap = need_warm + need_warm / 4;
+        SF_CUDA(c, cudaMalloc(&s.d_warm, sizeof(float) * cap));
+        s.cap_warm = cap;
+    }
+    const size_t need_bad = (size_t)n * lv.n_split;
+    if (need_bad > s.cap_bad) {
+        dfree(s.d_first_bad);
+        s.cap_bad = 0;
+        const size_t cap = need_bad + need_bad / 4;
+        SF_CUDA(c, cudaMalloc(&s.d_first_bad, sizeof(int32_t) * cap));
+        s.cap_bad = cap;
+    }
     return SFGPU_OK;
 }
 
@@ -713,10 +1002,18 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         c->ck_min_cols = std::max(128, opt->reserved[0]);
     if (opt->reserved[1] > 0)
         c->min_window = opt->reserved[1];
+    // warm-up of a piece of a split segment: 2q columns, rounded up to whole blocks
+    c->warm_blocks = (2 * opt->query_size + SF_BLOCK_COLS) / SF_BLOCK_COLS;
+    if (opt->reserved[2] > 0)
+        c->warm_blocks = opt->reserved[2];
+    c->force_level_len = opt->reserved[4];
     if (c->opt.n_slots <= 0)
         c->opt.n_slots = 2;
+    g_trace(opt->device, "sfgpu_create: begin");
     int rc = [&]() -> int {
         SF_CUDA(c, cudaSetDevice(opt->device));
+        SF_CUDA(c, cudaFree(0));
+        g_trace(opt->device, "sfgpu_create: CUDA context ready");
         const size_t nm = (size_t)1 << (2 * opt->kmer_size);
         SF_CUDA(c, cudaMalloc(&c->d_level_mean, sizeof(float) * nm));
         SF_CUDA(c, cudaMemcpy(c->d_level_mean, level_mean, sizeof(float) * nm, cudaMemcpyHostToDevice));
@@ -725,8 +1022,10 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             SF_CUDA(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             for (auto &e : s.ev)
                 SF_CUDA(c, cudaEventCreate(&e));
-            SF_CUDA(c, cudaMalloc(&s.d_counter, sizeof(unsigned int) * 2));
-            SF_CUDA(c, cudaMalloc(&s.d_counts, sizeof(int32_t) * 2));
+            SF_CUDA(c, cudaMalloc(&s.d_counter, sizeof(unsigned int) * 4));
+            SF_CUDA(c, cudaMalloc(&s.d_counts, sizeof(int32_t) * 4));
+            SF_CUDA(c, cudaMallocHost(&s.h_counts, sizeof(int32_t) * 4));
+            memset(s.h_counts, 0, sizeof(int32_t) * 4);
             memset(&s.timing, 0, sizeof s.timing);
         }
         const bool std_dtw = (opt->flags & SFGPU_DTW) != 0;
@@ -758,6 +1057,7 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         memcpy(g_err, keep, sizeof keep);
         return rc;
     }
+    g_trace(opt->device, "sfgpu_create: end (streams, model, occupancy queries)");
     *out = c;
     return SFGPU_OK;
 }
@@ -766,6 +1066,7 @@ void sfgpu_destroy(sfgpu_ctx *c)
 {
     if (!c)
         return;
+    g_trace(c->opt.device, "sfgpu_destroy: begin");
     cudaSetDevice(c->opt.device);
     for (auto &s : c->slots) {
         if (s.stream)
@@ -773,6 +1074,7 @@ void sfgpu_destroy(sfgpu_ctx *c)
         slot_free_buffers(s);
         dfree(s.d_counter);
         dfree(s.d_counts);
+        hfree(s.h_counts);
         for (auto &e : s.ev)
             if (e)
                 cudaEventDestroy(e);
@@ -781,6 +1083,7 @@ void sfgpu_destroy(sfgpu_ctx *c)
     }
     free_ref(c);
     dfree(c->d_level_mean);
+    g_trace(c->opt.device, "sfgpu_destroy: end");
     delete c;
 }
 
@@ -792,6 +1095,7 @@ int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_
     if (num_ref <= 0 || !bases || !base_off)
         return fail(c, SFGPU_EARG, "sfgpu_set_ref: empty reference");
     SF_CUDA(c, cudaSetDevice(c->opt.device));
+    g_trace(c->opt.device, "sfgpu_set_ref: begin");
     int rc = drop_ref(c);
     if (rc)
         return rc;
@@ -843,6 +1147,7 @@ int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_
     rc = layout_ref(c, num_ref, rlens.data(), !rna);
     if (rc)
         return rc;
+    g_trace(c->opt.device, "sfgpu_set_ref: layout done");
 
     const int64_t n_bases = base_off[num_ref];
     uint8_t *d_bases = nullptr;
@@ -886,6 +1191,7 @@ int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_
         return rc;
     }
     c->have_ref = true;
+    g_trace(c->opt.device, "sfgpu_set_ref: end (fill, stats, scale)");
     return SFGPU_OK;
 }
 

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.Opt) == 48
     assert C.sizeof(capi.Result) == 64
     assert capi.RESULT_DTYPE.itemsize == 64
-    assert C.sizeof(capi.Timing) == 48
+    assert C.sizeof(capi.Timing) == 64
 
 
 def test_no_device_is_an_error_not_a_fallback(lib):

@@ -234,6 +234,84 @@ def test_dtw_kernel_matches_oracle_random_and_ties(q, quant):
     oref.close()
 
 
+@pytest.mark.parametrize("q", [100, 250, 256, 300, 500])
+@pytest.mark.parametrize("quant", [0, 2])
+@pytest.mark.parametrize("warm", [0, 1])
+def test_split_segments_match_oracle(q, quant, warm):
+    """long segments cut into column pieces: every piece warms up behind a +INF column, its front
+    at the piece boundary is compared with its predecessor's, differing pieces are redone.  warm=0: the default
+    warm-up of 2q columns; warm=1: one block (63 columns < q), so that most fronts differ and the redo pass does
+    the work.  Random and tie-heavy inputs, ragged query lengths, queries cut out of the reference across piece
+    boundaries (score 0 hits whose chunk is shared by two pieces)."""
+    rng = np.random.default_rng(4000 * q + 10 * quant + warm)
+    lens = [20000, 700, 9000, 64 * 40 + 1, 5]
+    fwd = _rand_arrays(rng, lens, quant)
+    rev = _rand_arrays(rng, lens, quant)
+    qlens = [q, q, q, max(1, q - 1), max(1, q // 2), 25 if q > 25 else q, q, q]
+    queries = _rand_arrays(rng, qlens, quant)
+    for st in range(0, 20000 - q, 331):  # planted exact matches all along the long segment
+        src = fwd[0] if (st // 331) % 2 == 0 else rev[0]
+        queries.append(src[st:st + q].copy())
+    oref = H.OracleEventRef(fwd, rev)
+    want = [oref.align(x, 0) for x in queries]
+    for periods in (1, 3):
+        ctx = capi.Context(model(5), 5, query_size=q, ck_min_cols=128, min_window=16, warm_blocks=warm,
+                           piece_periods=periods)
+        ctx.set_ref_events(fwd, rev)
+        got = ctx.align_queries(queries)
+        t = ctx.timing(0)
+        assert t.piece_blocks > 0 and t.tasks_per_read > 2 * len(lens), (t.piece_blocks, t.tasks_per_read)
+        if warm == 1:
+            assert t.redone_pieces > 0
+        for i, o in enumerate(want):
+            g = got[i]
+            tag = (q, quant, warm, periods, i)
+            assert g["rid"] == o.rid, tag
+            assert "+-"[g["strand"]] == o.strand.decode(), tag
+            assert bits(g["score"]) == bits(o.score), tag
+            assert bits(g["score2"]) == bits(o.score2), tag
+            assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
+        # the same batch with splitting switched off gives the same bytes
+        ctx0 = capi.Context(model(5), 5, query_size=q, ck_min_cols=128, min_window=16, piece_periods=-1)
+        ctx0.set_ref_events(fwd, rev)
+        got0 = ctx0.align_queries(queries)
+        assert ctx0.timing(0).piece_blocks == 0
+        assert got0.tobytes() == got.tobytes()
+        ctx0.close()
+        ctx.close()
+    oref.close()
+
+
+def test_split_reads_through_whole_path_and_sam():
+    """reads (events + DTW + start coordinate + --sam paths) on a reference whose contigs are split into pieces,
+    forced redo included, against the oracle"""
+    k = 6
+    rng = np.random.default_rng(31)
+    seqs = [synth.random_sequence(30000, rng), synth.random_sequence(2500, rng)]
+    sigs, _ = synth.simulate_reads(seqs, k, model(k), 40, seed=32, bases_per_read=430)
+    sigs += synth.simulate_reads(seqs, k, model(k), 6, seed=33, bases_per_read=150, min_samples=700)[0]  # ragged queries
+    sc = [synth.DNA_SCALING] * len(sigs)
+    ref = H.OracleRef(seqs, model(k), k, 0, 250)
+    want = [H.orc_map(ref, s, c["digitisation"], c["offset"], c["range"], 0, 250, 50) for s, c in zip(sigs, sc)]
+    base = None
+    for warm, periods in ((0, 1), (1, 2), (0, 0)):
+        ctx = capi.Context(model(k), k, flags=capi.SFGPU_SAM, ck_min_cols=256, warm_blocks=warm, piece_periods=periods)
+        ctx.set_ref(seqs)
+        got = ctx.map_batch(sigs, sc)
+        t = ctx.timing(0)
+        assert t.piece_blocks > 0
+        if warm == 1:
+            assert t.redone_pieces > 0
+        for i, o in enumerate(want):
+            assert_hit_equal(got[i], o, ("split", warm, periods, i), 0, 250, 50)
+        paths, _, _ = ctx.collect_paths(0, got)
+        blob = got.tobytes() + b"".join(b"-" if p is None else p[0].tobytes() + p[1].tobytes() for p in paths)
+        base = base or blob
+        assert blob == base
+        ctx.close()
+    ref.close()
+
+
 @pytest.mark.parametrize("q", [30, 250, 375])
 @pytest.mark.parametrize("quant", [0, 2])
 def test_std_dtw_kernel_matches_oracle(q, quant):

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--ref-len", type=int, default=1_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("-K", type=int, default=0)
+    ap.add_argument("--trace", default="", help="write the CLI's stderr (--verbose 5, SFGPU_TRACE=1) to this file")
     args = ap.parse_args()
     B.build_all()
     d = os.path.join(synth.tmpdir(), "cli_e2e")
@@ -43,7 +44,10 @@ def main():
     t0 = time.perf_counter()
     r = subprocess.run([B.CLI, "dtw", os.path.join(d, "ref.fa"), os.path.join(d, "reads.blow5"), "--kmer-model",
                         os.path.join(d, "model.txt"), "-K", str(K), "-B", "100G", "-t", str(os.cpu_count() or 8), "--gpus", str(args.gpus),
-                        "-o", os.path.join(d, "gpu.paf")], capture_output=True, text=True)
+                        "-o", os.path.join(d, "gpu.paf")] + (["--verbose", "5"] if args.trace else []),
+                       capture_output=True, text=True, env=dict(os.environ, **({"SFGPU_TRACE": "1"} if args.trace else {})))
+    if args.trace:
+        open(args.trace, "w").write(r.stderr)
     out["b200_wall_s"] = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-3000:]
     for line in r.stderr.splitlines():
