@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsfgpu.so")
+# SFGPU_LIB: another build of the same ABI (A/B experiments); the default is the in-tree library
+LIB_PATH = os.environ.get("SFGPU_LIB") or os.path.join(PKG, "libsfgpu.so")
 
 SFGPU_RNA, SFGPU_DTW, SFGPU_INV, SFGPU_REF, SFGPU_END, SFGPU_SAM = 0x001, 0x002, 0x004, 0x010, 0x020, 0x100
 

@@ -66,7 +66,21 @@ struct sf_dtw_args {
 };
 
 // ring (float2 x 128) + last-row buffer (2 values per macro-step; 2R in the generic block)
-__host__ __device__ inline int sf_smem_floats_per_warp(int R) { return 2 * SF_RING_PAIRS + 64 * R; }
+// Per-warp task state that only the per-block epilogue touches (chunk bookkeeping, running top-2, checkpoint
+// schedule).  It lives in shared memory, read through a volatile pointer, so that across the unrolled macro-steps
+// the registers hold nothing but the DTW state: with this state in registers ptxas ran out of room to interleave
+// the two column chains (measured: -8 % on the 1 Mb shape).
+enum {
+    SF_ST_CLO, SF_ST_CHI, SF_ST_CHUNK, SF_ST_SI, SF_ST_LO, SF_ST_HI,
+    SF_ST_EVT,    // block at whose end a checkpoint or the warm front is due (0x7fffffff: none)
+    SF_ST_CK, SF_ST_PFLAGS, SF_ST_PIDX,
+    SF_ST_READ,   // + half
+    SF_ST_TOP = 12, // + 5 * half: s1, s2, seg, chunk, pos of the running best
+    SF_ST_VALID = 22, // + half: does this half carry a read of its own (pair layout, odd lists)
+    SF_ST_QLEN = 24,
+    SF_ST_WORDS = 32
+};
+__host__ __device__ inline int sf_smem_floats_per_warp(int R) { return 2 * SF_RING_PAIRS + 64 * R + SF_ST_WORDS; }
 // one wavefront checkpoint: L[R], dprev, botA per lane
 __host__ __device__ inline int sf_ckpt_floats(int R) { return (R + 2) * 32; }
 
@@ -214,6 +228,153 @@ __device__ __forceinline__ bool sf_fronts_equal(const sf_dtw_args &a, const int 
     return !__any_sync(0xffffffffu, ne);
 }
 
+// ---- pieces of the per-block epilogue, shared by the two layouts (W lanes per read) ----
+
+// Task set-up of the state words (lane 0 writes, everyone syncs): chunk bookkeeping of the first segment, or of
+// the piece's own columns; the block of the first checkpoint / warm front.  Returns nothing; the caller reads the
+// state back through `st`.
+template <bool STD, bool RESUME>
+__device__ __forceinline__ void sf_task_state_init(volatile int *st, const sf_dtw_args &a, const sf_piece &pc, const sf_group &grp,
+                                                   const int pidx, const int qlen, const int lq, const int lane)
+{
+    if (lane == 0) {
+        const sf_seg seg = a.segs[grp.seg0];
+        const int lo = (int)(seg.off - grp.begin);
+        int hi = lo + seg.rlen;
+        int chunk = 0, clo = STD ? hi - 1 : lo, ck = 0;
+        if (pc.flags & 3) { // a piece of a split segment (single-segment group, never STD): the last row of its own
+                            // blocks [b0, b1) is columns [64 b0 - 2 lq, 64 b1 - 2 lq)
+            if (pc.flags & 2)
+                hi = min(hi, SF_BLOCK_COLS * pc.b1 - 2 * lq);
+            if (pc.flags & 1) {
+                clo = SF_BLOCK_COLS * pc.b0 - 2 * lq;
+                chunk = (clo - lo) / qlen;
+                ck = pc.b0 / grp.ck_every;
+            }
+        }
+        st[SF_ST_CLO] = clo;
+        st[SF_ST_CHI] = STD ? hi : min(lo + (chunk + 1) * qlen, hi);
+        st[SF_ST_CHUNK] = chunk;
+        st[SF_ST_SI] = grp.seg0;
+        st[SF_ST_LO] = lo;
+        st[SF_ST_HI] = hi;
+        st[SF_ST_CK] = ck;
+        // bit 0: has a predecessor, bit 1: has a successor, bit 2: the head edge is still to come
+        st[SF_ST_PFLAGS] = pc.flags | ((pc.flags & 1) << 2);
+        st[SF_ST_PIDX] = pidx;
+        int evt = 0x7fffffff;
+        if (grp.ck_every > 0 && ck < grp.n_ck)
+            evt = (ck + 1) * grp.ck_every - 1;
+        if (!RESUME && (pc.flags & 1))
+            evt = pc.b0 - 1; // the warm front comes first
+        st[SF_ST_EVT] = evt;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            st[SF_ST_TOP + 5 * h + 0] = __float_as_int(SF_INF);
+            st[SF_ST_TOP + 5 * h + 1] = __float_as_int(SF_INF);
+            st[SF_ST_TOP + 5 * h + 2] = -1;
+            st[SF_ST_TOP + 5 * h + 3] = 0;
+            st[SF_ST_TOP + 5 * h + 4] = -1;
+        }
+    }
+    __syncwarp();
+}
+
+// A chunk is complete: (m, mp) = its first strict minimum for this lane's read (already reduced over the read's
+// lanes).  Books it -- as the head / tail edge of a piece or into the running top-2 of read `half` -- and opens the
+// next chunk.  `writer`: the one lane of the read that stores.
+template <bool STD>
+__device__ __forceinline__ void sf_chunk_done(volatile int *st, const sf_dtw_args &a, const float m, const int mp, const int half,
+                                              const bool writer, const int lane)
+{
+    const int pidx = st[SF_ST_PIDX];
+    const bool valid = st[SF_ST_VALID + half] != 0;
+    const int qlen = st[SF_ST_QLEN];
+    const int pflags = st[SF_ST_PFLAGS];
+    int chunk = st[SF_ST_CHUNK], si = st[SF_ST_SI], lo = st[SF_ST_LO], hi = st[SF_ST_HI];
+    const int chi = st[SF_ST_CHI];
+    const int pos = mp >= 0 ? mp - lo : -1;
+    if (pflags & 4) { // the chunk cut by the piece's start: reported apart (head edge)
+        if (writer && valid) {
+            sf_taskres *out = a.res + (size_t)st[SF_ST_READ + half] * a.n_pieces + pidx;
+            out->hmin = m; out->hpos = pos; out->hchunk = chunk;
+        }
+    } else if ((pflags & 2) && chi >= hi) { // the chunk cut by the piece's end (tail edge)
+        if (writer && valid) {
+            sf_taskres *out = a.res + (size_t)st[SF_ST_READ + half] * a.n_pieces + pidx;
+            out->tmin = m; out->tpos = pos; out->tchunk = chunk;
+        }
+    } else if (writer) { // update_aln(): a later candidate with an equal score ranks better
+        volatile int *t = st + SF_ST_TOP + 5 * half;
+        const float s1 = __int_as_float(t[0]), s2 = __int_as_float(t[1]);
+        if (m <= s1) {
+            t[1] = __float_as_int(s1); t[0] = __float_as_int(m); t[2] = si; t[3] = chunk; t[4] = pos;
+        } else if (m < s2) {
+            t[1] = __float_as_int(m);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int clo = chi;
+        chunk++;
+        if (clo >= hi) {
+            const sf_group grp = a.groups[a.pieces[pidx].gid];
+            si++;
+            chunk = 0;
+            if (si < grp.seg0 + grp.nseg) {
+                const sf_seg seg = a.segs[si];
+                lo = (int)(seg.off - grp.begin);
+                hi = lo + seg.rlen;
+                clo = STD ? hi - 1 : lo;
+            } else {
+                clo = 0x7fffffff;
+                hi = 0x7fffffff;
+            }
+        }
+        st[SF_ST_CLO] = clo;
+        st[SF_ST_CHI] = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
+        st[SF_ST_CHUNK] = chunk;
+        st[SF_ST_SI] = si;
+        st[SF_ST_LO] = lo;
+        st[SF_ST_HI] = hi;
+        st[SF_ST_PFLAGS] = pflags & ~4;
+    }
+    __syncwarp();
+}
+
+// End of block b == st[SF_ST_EVT]: write the regular checkpoint and / or the piece's warm front (layout
+// [R+2][W]: L[r], dprev, botA per lane), then schedule the next one.
+template <int R, int W, bool RESUME>
+__device__ __forceinline__ void sf_block_event(volatile int *st, const sf_dtw_args &a, const int b, const int half,
+                                               const int ll, const int lane, const float (&L)[R], const float dprev, const float botA)
+{
+    const int read = st[SF_ST_READ + half];
+    const bool valid = st[SF_ST_VALID + half] != 0;
+    const sf_piece pc = a.pieces[st[SF_ST_PIDX]];
+    const sf_group grp = a.groups[pc.gid];
+    int ck = st[SF_ST_CK];
+    float *c = nullptr;
+    if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
+        c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
+        ck++;
+    } else if (!RESUME && (pc.flags & 1) && b + 1 == pc.b0) {
+        c = a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats;
+    }
+    if (c && valid) {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            c[r * W + ll] = L[r];
+        c[R * W + ll] = dprev;
+        c[(R + 1) * W + ll] = botA;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        st[SF_ST_CK] = ck;
+        st[SF_ST_EVT] = (grp.ck_every > 0 && ck < grp.n_ck) ? (ck + 1) * grp.ck_every - 1 : 0x7fffffff;
+    }
+    __syncwarp();
+}
+
 // One (read, piece) task of the warp-per-read layout.  RESUME: start at the piece's boundary from the checkpoint the
 // predecessor left there (redo of a piece whose warm front did not verify) instead of warming up.
 template <int R, bool STD, bool RESUME>
@@ -221,12 +382,13 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
                                               float2 *ring, float *last)
 {
     const unsigned full = 0xffffffffu;
+    volatile int *st = reinterpret_cast<volatile int *>(last + 64 * R);
     const sf_piece pc = a.pieces[pidx];
     const sf_group grp = a.groups[pc.gid];
-    sf_taskres *out = a.res + (size_t)read * a.n_pieces + pidx;
     const int qlen = a.info[read].qlen;
     if (qlen <= 0) {
         if (lane == 0) {
+            sf_taskres *out = a.res + (size_t)read * a.n_pieces + pidx;
             out->s1 = SF_INF; out->s2 = SF_INF; out->seg = -1; out->chunk = 0; out->pos = -1;
             out->hmin = SF_INF; out->hpos = -1; out->hchunk = -1; out->tmin = SF_INF; out->tpos = -1; out->tchunk = -2;
         }
@@ -237,14 +399,12 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
     const bool is_lq = lane == lq;
     const bool fast = rq == sf_fast_rq(R); // warp-uniform
     const int nz = lane != 0;
-    // bit 0: has a predecessor, bit 1: has a successor, bit 2: the head edge is still to come
-    int pflags = pc.flags | ((pc.flags & 1) << 2);
 
     const float *y = a.stream + grp.begin;
     const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
     // the last column (n_pos-1) is in pair (n_pos-1)/2 and reaches lane lq lq macro-steps later
-    const int b_end = (pflags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
-    const int b_first = RESUME ? pc.b0 : ((pflags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
+    const int b_end = (pc.flags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
+    const int b_first = RESUME ? pc.b0 : ((pc.flags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
 
     // query rows of this lane; rows past qlen are padding (finite, never read back)
     float x[R], L[R];
@@ -284,31 +444,15 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
         ring[cur] = v; ring[cur + 64] = v;
         ring[prv] = pv; ring[prv + 64] = pv;
     }
-    __syncwarp();
-
-    // chunk bookkeeping (warp-uniform)
-    int si = grp.seg0;
-    const int si_end = grp.seg0 + grp.nseg;
-    sf_seg seg = a.segs[si];
-    int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
-    int chunk = 0;
-    int clo = STD ? hi - 1 : lo;
-    int ck = 0;
-    if (pflags & 3) { // a piece of a split segment (single-segment group, never STD): the last row of its own
-                      // blocks [b0, b1) is columns [64 b0 - 2 lq, 64 b1 - 2 lq)
-        if (pflags & 2)
-            hi = min(hi, SF_BLOCK_COLS * pc.b1 - 2 * lq);
-        if (pflags & 1) {
-            clo = SF_BLOCK_COLS * pc.b0 - 2 * lq;
-            chunk = (clo - lo) / qlen;
-            ck = pc.b0 / grp.ck_every;
-        }
+    if (lane == 0) {
+        st[SF_ST_READ] = read;
+        st[SF_ST_VALID] = 1;
+        st[SF_ST_QLEN] = qlen;
     }
-    int chi = STD ? hi : min(lo + (chunk + 1) * qlen, hi);
+    sf_task_state_init<STD, RESUME>(st, a, pc, grp, pidx, qlen, lq, lane);
+
     float rmin = SF_INF; // per lane running minimum of the open chunk
     int rpos = -1;
-    float s1 = SF_INF, s2 = SF_INF;
-    int bseg = -1, bchunk = 0, bpos = -1;
 
     for (int b = b_first; b < b_end; b++) {
         // prefetch the next 64 reference events; published after the 32 macro-steps below
@@ -337,6 +481,7 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
                 v0 = v.x; v1 = v.y;
             }
             for (;;) {
+                const int clo = st[SF_ST_CLO], chi = st[SF_ST_CHI];
                 if (pos0 >= clo && pos0 < chi && v0 < rmin) {
                     rmin = v0;
                     rpos = pos0;
@@ -359,57 +504,16 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
                         mp = op;
                     }
                 }
-                if (pflags & 4) { // the chunk cut by the piece's start: reported apart (head edge)
-                    if (lane == 0) { out->hmin = m; out->hpos = mp >= 0 ? mp - lo : -1; out->hchunk = chunk; }
-                    pflags &= ~4;
-                } else if ((pflags & 2) && chi >= hi) { // the chunk cut by the piece's end (tail edge)
-                    if (lane == 0) { out->tmin = m; out->tpos = mp >= 0 ? mp - lo : -1; out->tchunk = chunk; }
-                } else if (m <= s1) { // update_aln(): a later candidate with an equal score ranks better
-                    s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
-                } else if (m < s2) {
-                    s2 = m;
-                }
+                sf_chunk_done<STD>(st, a, m, mp, 0, lane == 0, lane);
                 rmin = SF_INF;
                 rpos = -1;
-                clo = chi;
-                chunk++;
-                if (clo >= hi) {
-                    si++;
-                    chunk = 0;
-                    if (si < si_end) {
-                        seg = a.segs[si];
-                        lo = (int)(seg.off - grp.begin);
-                        hi = lo + seg.rlen;
-                        clo = STD ? hi - 1 : lo;
-                    } else {
-                        clo = 0x7fffffff;
-                        hi = 0x7fffffff;
-                    }
-                }
-                chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
             }
         }
 
         // ---- checkpoint of the skewed wavefront (for the start-coordinate pass; the one at a piece's end is also
-        //      what the next piece's warm front is verified against) ----
-        if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-            float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                c[r * 32 + lane] = L[r];
-            c[R * 32 + lane] = dprev;
-            c[(R + 1) * 32 + lane] = botA;
-            ck++;
-        }
-        // ---- warm front: the state this piece reached at its boundary ----
-        if (!RESUME && (pflags & 1) && b + 1 == pc.b0) {
-            float *c = a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats;
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                c[r * 32 + lane] = L[r];
-            c[R * 32 + lane] = dprev;
-            c[(R + 1) * 32 + lane] = botA;
-        }
+        //      what the next piece's warm front is verified against), warm front of a piece ----
+        if (b == st[SF_ST_EVT])
+            sf_block_event<R, 32, RESUME>(st, a, b, 0, lane, lane, L, dprev, botA);
 
         // publish block b+1 of the reference events (overwrites block b-1)
         {
@@ -422,8 +526,11 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
     }
 
     if (lane == 0) {
-        out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
+        sf_taskres *out = a.res + (size_t)st[SF_ST_READ] * a.n_pieces + st[SF_ST_PIDX];
+        volatile int *t = st + SF_ST_TOP;
+        out->s1 = __int_as_float(t[0]); out->s2 = __int_as_float(t[1]); out->seg = t[2]; out->chunk = t[3]; out->pos = t[4];
     }
+    __syncwarp();
 }
 
 // FIX: the redo pass.  Walks the pieces of every (read, split group) that sf_verify_kernel flagged, from the first
@@ -487,7 +594,7 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 #define SF_PAIR_LANES 16
 // last-row staging of one read: 64 floats + 4 of padding, so that the two storing lanes hit different banks
 #define SF_PAIR_LAST 68
-__host__ __device__ inline int sf_pair_smem_floats_per_warp() { return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST; }
+__host__ __device__ inline int sf_pair_smem_floats_per_warp() { return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST + SF_ST_WORDS; }
 
 // One (pair of reads, piece) task.  `read` / `valid` are per half; RESUME as in sf_score_task.
 template <int R, bool STD, int RQ, bool RESUME>
@@ -496,6 +603,7 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
 {
     constexpr int W = SF_PAIR_LANES;
     const unsigned full = 0xffffffffu;
+    volatile int *st = reinterpret_cast<volatile int *>(last + 2 * SF_PAIR_LAST);
     const int ll = lane & (W - 1);  // lane inside the read
     const int half = lane / W;      // which read of the pair
     const int qlen = a.q_full;
@@ -504,13 +612,11 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
     const int nz = ll != 0;
     const sf_piece pc = a.pieces[pidx];
     const sf_group grp = a.groups[pc.gid];
-    sf_taskres *out = a.res + (size_t)read * a.n_pieces + pidx;
-    int pflags = pc.flags | ((pc.flags & 1) << 2); // see sf_score_task
 
     const float *y = a.stream + grp.begin;
     const int n_pos = (int)(grp.end - grp.begin); // includes the leading sentinel
-    const int b_end = (pflags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
-    const int b_first = RESUME ? pc.b0 : ((pflags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
+    const int b_end = (pc.flags & 2) ? pc.b1 : ((n_pos - 1) / 2 + lq + 32) >> 5;
+    const int b_first = RESUME ? pc.b0 : ((pc.flags & 1) ? max(0, pc.b0 - a.warm_blocks) : 0);
 
     float x[R], L[R];
     const float *q = a.queries + (size_t)read * a.q_cap;
@@ -546,29 +652,16 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
         ring[cur] = v; ring[cur + 64] = v;
         ring[prv] = pv; ring[prv + 64] = pv;
     }
-    __syncwarp();
-
-    // chunk bookkeeping: shared by the two reads (same query length, same segments)
-    int si = grp.seg0;
-    const int si_end = grp.seg0 + grp.nseg;
-    sf_seg seg = a.segs[si];
-    int lo = (int)(seg.off - grp.begin), hi = lo + seg.rlen;
-    int chunk = 0;
-    int clo = STD ? hi - 1 : lo;
-    int ck = 0;
-    if (pflags & 3) {
-        if (pflags & 2)
-            hi = min(hi, SF_BLOCK_COLS * pc.b1 - 2 * lq);
-        if (pflags & 1) {
-            clo = SF_BLOCK_COLS * pc.b0 - 2 * lq;
-            chunk = (clo - lo) / qlen;
-            ck = pc.b0 / grp.ck_every;
-        }
+    // chunk bookkeeping is shared by the two reads (same query length, same segments); the running best is per read
+    if (ll == 0) {
+        st[SF_ST_READ + half] = read;
+        st[SF_ST_VALID + half] = valid ? 1 : 0;
+        st[SF_ST_QLEN] = qlen;
     }
-    int chi = STD ? hi : min(lo + (chunk + 1) * qlen, hi);
-    // per read: the lanes of a half track the last row of their own read
-    float rmin = SF_INF, s1 = SF_INF, s2 = SF_INF;
-    int rpos = -1, bseg = -1, bchunk = 0, bpos = -1;
+    sf_task_state_init<STD, RESUME>(st, a, pc, grp, pidx, qlen, lq, lane);
+
+    float rmin = SF_INF;
+    int rpos = -1;
 
     for (int b = b_first; b < b_end; b++) {
         const int nidx = SF_BLOCK_COLS * (b + 1) + 2 * lane;
@@ -586,6 +679,7 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
             const int pos0 = p0 + 4 * ll;
             const float4 v = *reinterpret_cast<const float4 *>(last + SF_PAIR_LAST * half + 4 * ll);
             for (;;) {
+                const int clo = st[SF_ST_CLO], chi = st[SF_ST_CHI];
                 if (pos0 >= clo && pos0 < chi && v.x < rmin) { rmin = v.x; rpos = pos0; }
                 if (pos0 + 1 >= clo && pos0 + 1 < chi && v.y < rmin) { rmin = v.y; rpos = pos0 + 1; }
                 if (pos0 + 2 >= clo && pos0 + 2 < chi && v.z < rmin) { rmin = v.z; rpos = pos0 + 2; }
@@ -603,58 +697,15 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
                         mp = op;
                     }
                 }
-                if (pflags & 4) { // head edge of a piece
-                    if (ll == 0 && valid) { out->hmin = m; out->hpos = mp >= 0 ? mp - lo : -1; out->hchunk = chunk; }
-                    pflags &= ~4;
-                } else if ((pflags & 2) && chi >= hi) { // tail edge of a piece
-                    if (ll == 0 && valid) { out->tmin = m; out->tpos = mp >= 0 ? mp - lo : -1; out->tchunk = chunk; }
-                } else if (m <= s1) {
-                    s2 = s1; s1 = m; bseg = si; bchunk = chunk; bpos = mp >= 0 ? mp - lo : -1;
-                } else if (m < s2) {
-                    s2 = m;
-                }
+                sf_chunk_done<STD>(st, a, m, mp, half, ll == 0, lane);
                 rmin = SF_INF;
                 rpos = -1;
-                clo = chi;
-                chunk++;
-                if (clo >= hi) {
-                    si++;
-                    chunk = 0;
-                    if (si < si_end) {
-                        seg = a.segs[si];
-                        lo = (int)(seg.off - grp.begin);
-                        hi = lo + seg.rlen;
-                        clo = STD ? hi - 1 : lo;
-                    } else {
-                        clo = 0x7fffffff;
-                        hi = 0x7fffffff;
-                    }
-                }
-                chi = (clo == 0x7fffffff) ? 0x7fffffff : (STD ? hi : min(clo + qlen, hi));
             }
         }
 
-        // ---- checkpoint (half-warp layout), one per read ----
-        if (grp.ck_every > 0 && ck < grp.n_ck && (b + 1) == (ck + 1) * grp.ck_every) {
-            if (valid) {
-                float *c = a.ckpt + ((size_t)read * a.ck_per_read + grp.ck_prefix + ck) * (size_t)a.ck_floats;
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    c[r * W + ll] = L[r];
-                c[R * W + ll] = dprev;
-                c[(R + 1) * W + ll] = botA;
-            }
-            ck++;
-        }
-        // ---- warm front of a piece ----
-        if (!RESUME && (pflags & 1) && b + 1 == pc.b0 && valid) {
-            float *c = a.warm + ((size_t)read * a.n_warm + pc.widx) * (size_t)a.ck_floats;
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                c[r * W + ll] = L[r];
-            c[R * W + ll] = dprev;
-            c[(R + 1) * W + ll] = botA;
-        }
+        // ---- checkpoint (half-warp layout, one per read) / warm front of a piece ----
+        if (b == st[SF_ST_EVT])
+            sf_block_event<R, W, RESUME>(st, a, b, half, ll, lane, L, dprev, botA);
 
         {
             const int slot = ((b + 1) & 1) * 32 + lane;
@@ -665,9 +716,12 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
         __syncwarp();
     }
 
-    if (ll == 0 && valid) {
-        out->s1 = s1; out->s2 = s2; out->seg = bseg; out->chunk = bchunk; out->pos = bpos;
+    if (ll == 0 && st[SF_ST_VALID + half]) {
+        sf_taskres *out = a.res + (size_t)st[SF_ST_READ + half] * a.n_pieces + st[SF_ST_PIDX];
+        volatile int *t = st + SF_ST_TOP + 5 * half;
+        out->s1 = __int_as_float(t[0]); out->s2 = __int_as_float(t[1]); out->seg = t[2]; out->chunk = t[3]; out->pos = t[4];
     }
+    __syncwarp();
 }
 
 template <int R, bool STD, int RQ, bool FIX = false>

@@ -115,3 +115,30 @@ def test_eval_usage_and_errors(cli, tmp_path):
     bad.write_text("r1\t100\t0\t50\t+\tchr\n")
     r = run(cli, "eval", str(bad), str(bad))
     assert r.returncode != 0 and "malformed PAF" in r.stderr
+
+
+@pytest.mark.refbin
+def test_patched_reference_keeps_its_cpu_path_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/sigfish_acc.patch, applied and compiled by oracle/Makefile (ref_acc): with --accel=no the binary
+    is the reference (golden PAF from the CPU code); with --accel=yes and no device it exits with the library's
+    error instead of falling back."""
+    import json
+    acc = os.path.join(H.ORACLE_DIR, "_ref", "sigfish_acc")
+    if not os.path.exists(acc):
+        pytest.skip("oracle/_ref/sigfish_acc not built (needs /root/reference at build time)")
+    patch = open(os.path.join(H.ROOT, "integration", "sigfish_acc.patch")).read()
+    for sym in ("sfgpu_create", "sfgpu_set_ref", "sfgpu_submit_reads", "sfgpu_collect", "sfgpu_collect_paths", "sfgpu_destroy"):
+        assert sym in patch
+    c = json.load(open(os.path.join(H.GOLDEN, "cases.json")))["dna_sp1_default"]
+    names, seqs = H.case_fasta(c)
+    ids, sigs, sc = H.case_reads(c)
+    fa, s5, mf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.blow5"), str(tmp_path / "model.txt")
+    synth.write_fasta(fa, names, seqs)
+    synth.write_blow5(s5, ids, sigs, scalings=sc)
+    synth.write_model_file(mf, c["k"], *synth.make_model(c["k"]))
+    r = subprocess.run([acc, "dtw", fa, s5, "--kmer-model", mf, "--accel=no"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    assert r.stdout == open(os.path.join(H.GOLDEN, "paf", "dna_sp1_default.paf")).read()
+    if capi.lib().sfgpu_device_count() == 0:
+        r = subprocess.run([acc, "dtw", fa, s5, "--kmer-model", mf, "--accel=yes"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr and r.stdout == ""

@@ -206,3 +206,54 @@ def test_cli_fuzz_matches_oracle_paf_and_sam(cli, tmp_path, seed):
         out, _ = _run(cli, c, fa, s5, mf, ["--sam"])
         out = "".join(l for l in out.splitlines(keepends=True) if not l.startswith("@PG"))
         assert out == H.oracle_sam(names, seqs, mean, k, ids, sigs, scs, oflags, q, p), (flags, q, p)
+
+
+# ---------------------------------------------------------------- the reference's own host code over libsfgpu.so
+
+REF_ACC_BIN = os.path.join(H.ORACLE_DIR, "_ref", "sigfish_acc")
+ACC_CASES = ["dna_sp1_default", "rna_sequin_default", "dna_synth48", "dna_sp1_from_end", "dna_short_reads", "dna_r10_k9",
+             "rna_sequin_invert", "rna_sequin_dtw_std", "rna_sequin_q500_auto", "rna_tail24_auto", "rna004_tx2000_invert"]
+
+
+def _run_acc(c, fa, reads, mf, extra=()):
+    cmd = [REF_ACC_BIN, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"]), "-t", "4"] + \
+        H.flags_to_cli(c["flags"]) + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout, r.stderr
+
+
+@pytest.mark.parametrize("case", ACC_CASES)
+def test_reference_binary_with_accelerator_seam_matches_golden(tmp_path, case):
+    """integration/sigfish_acc.patch applied to the reference (oracle/Makefile: ref_acc) = the reference's `make acc=1`
+    build with its dormant accelerator hooks bound to libsfgpu.so.  Its own main(), slow5lib loading, work_db(parse_single),
+    paf_str() and output_db() run unchanged; events, query window, DTW and hit selection come from the GPU.  The PAF must
+    equal what the same sources print on the CPU (tests/golden/paf)."""
+    if not os.path.exists(REF_ACC_BIN):
+        pytest.skip("oracle/_ref/sigfish_acc not built (needs /root/reference at build time)")
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, err = _run_acc(c, fa, reads, mf, ["--accel=yes"])
+    assert "Initialising accelator" in err
+    assert out == open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read()
+
+
+@pytest.mark.parametrize("case", ["dna_synth48", "rna_sequin_default", "rna_tail24_auto"])
+def test_reference_binary_with_accelerator_seam_sam(tmp_path, case):
+    """--sam through the patched reference: sfgpu_collect_paths() feeds the reference's own path_to_map() / sam_str()"""
+    if not os.path.exists(REF_ACC_BIN):
+        pytest.skip("oracle/_ref/sigfish_acc not built")
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, _ = _run_acc(c, fa, reads, mf, ["--accel=yes", "--sam"])
+    want = open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()
+    strip = lambda t: "".join(l for l in t.splitlines(keepends=True) if not l.startswith("@PG"))
+    assert strip(out) == strip(want)
+
+
+def test_reference_binary_accel_no_is_the_cpu_path(tmp_path):
+    """the same patched binary with --accel=no runs the reference's CPU code: the seam is a switch, not a fork"""
+    if not os.path.exists(REF_ACC_BIN):
+        pytest.skip("oracle/_ref/sigfish_acc not built")
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "blow5")
+    out, err = _run_acc(c, fa, reads, mf, ["--accel=no"])
+    assert "Initialising accelator" not in err
+    assert out == open(os.path.join(H.GOLDEN, "paf", "dna_sp1_default.paf")).read()

@@ -171,7 +171,7 @@ def test_batch_slots_and_resubmit_are_deterministic():
     ctx.submit_reads(1, sigs, sc)  # one pointer per read instead of one flat buffer
     assert ctx.collect(1).tobytes() == b.tobytes()
     t = ctx.timing(0)
-    assert t.dtw_launches in (1, 2) and t.cells > 0 and t.dtw_ms > 0  # 2: pair kernel + warp-per-read kernel
+    assert 1 <= t.dtw_launches <= 4 and t.cells > 0 and t.dtw_ms > 0  # pair kernel + warp-per-read kernel (+ their redo passes)
     ctx.close()
 
 
@@ -752,7 +752,7 @@ def test_paired_and_unpaired_layouts_agree(q, std):
                 ctx.set_ref_events(fwd, rev)
                 outs.append(ctx.align_queries(queries).tobytes())
                 got = ctx.align_queries(queries)
-                assert ctx.timing(0).dtw_launches == (1 if nopair else 2)
+                assert ctx.timing(0).dtw_launches in ((1, 2) if nopair else (2, 4))  # + the redo passes when segments are split
                 ctx.close()
         assert all(o == outs[0] for o in outs), (q, std, n_full)
         for i, x in enumerate(queries):
