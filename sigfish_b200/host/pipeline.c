@@ -394,19 +394,18 @@ void parse_db(core_t *core, db_t *db)
     core->parse_time += sf_realtime() - t0;
 }
 
-/* Splits n_rec reads into G contiguous ranges [begin[g], begin[g+1]) holding about the same number of
- * samples each (the per-read device work is dominated by the fixed-size DTW, the copy by the samples; a
+/* Splits n_rec reads into G contiguous ranges [begin[g], begin[g+1]) of about the same total weight (a
  * contiguous split keeps the output in input order with a plain concatenation). */
-void sf_shard_ranges(int32_t n_rec, const int64_t *n_samples, int32_t G, int32_t *begin)
+void sf_shard_ranges(int32_t n_rec, const int64_t *weight, int32_t G, int32_t *begin)
 {
     int64_t total = 0;
     for (int i = 0; i < n_rec; i++)
-        total += n_samples[i];
+        total += weight[i];
     int64_t acc = 0;
     int g = 0;
     begin[0] = 0;
     for (int i = 0; i < n_rec && g + 1 < G; i++) {
-        acc += n_samples[i];
+        acc += weight[i];
         while (g + 1 < G && acc * G >= total * (g + 1)) {
             g++;
             begin[g] = i + 1;
@@ -438,14 +437,19 @@ static void *gpu_submit_worker(void *p)
 
 void submit_db(core_t *core, db_t *db)
 {
-    /* shards: contiguous read ranges with about the same number of samples each */
+    /* shards: contiguous read ranges of about the same estimated device work.  A read costs its DTW, which does not
+     * depend on its length (query_size rows x every reference column: the unit here is one DTW cell), plus the
+     * copy and event detection of its samples (~640 cell times per sample: 2 bytes over PCIe against 8 TCUPS).
+     * Balancing samples alone, as the first version did, gives a GPU with a few long reads much less DTW work than
+     * one with many short reads, and the batch waits for the slowest GPU. */
     const int G = core->num_gpus;
     {
-        int64_t *lens = (int64_t *)malloc(sizeof(int64_t) * (size_t)(db->n_rec > 0 ? db->n_rec : 1));
+        int64_t *w = (int64_t *)malloc(sizeof(int64_t) * (size_t)(db->n_rec > 0 ? db->n_rec : 1));
+        const int64_t dtw = (int64_t)core->opt.query_size * sfgpu_ref_columns(core->gpu[0]);
         for (int i = 0; i < db->n_rec; i++)
-            lens[i] = (int64_t)db->rec[i].len_raw_signal;
-        sf_shard_ranges(db->n_rec, lens, G, db->shard_begin);
-        free(lens);
+            w[i] = db->rec[i].len_raw_signal > 0 ? dtw + 640 * (int64_t)db->rec[i].len_raw_signal : 1;
+        sf_shard_ranges(db->n_rec, w, G, db->shard_begin);
+        free(w);
     }
     int g;
 

@@ -172,7 +172,7 @@ void free_db(db_t *db);
 void free_core(core_t *core, opt_t opt);
 
 /* contiguous read ranges per GPU with equal sample counts: begin[0..G] */
-void sf_shard_ranges(int32_t n_rec, const int64_t *n_samples, int32_t G, int32_t *begin);
+void sf_shard_ranges(int32_t n_rec, const int64_t *weight, int32_t G, int32_t *begin);
 
 /* writes the @SQ header lines of --sam output (src/dtw_main.c:118-123) */
 void sam_hdr_wr(const refsynth_t *ref);

@@ -105,6 +105,7 @@ int sfgpu_timing(sfgpu_ctx *c, int32_t slot, sfgpu_timing_t *t)
 }
 
 int32_t sfgpu_wave_reads(const sfgpu_ctx *c) { (void)c; return 4144; }
+int64_t sfgpu_ref_columns(const sfgpu_ctx *c) { (void)c; return 2 * 999992; }
 const char *sfgpu_strerror(const sfgpu_ctx *c) { (void)c; return "null device"; }
 
 void sfgpu_destroy(sfgpu_ctx *c)
