@@ -433,13 +433,16 @@ def main():
     torch.cuda.empty_cache()
     files = None
     if not args.no_files:
+        # the other ranks wait on the CPU: an NCCL barrier would keep a kernel spinning on their GPUs, which the
+        # command line started by rank 0 is about to use
         R.barrier()
+        R.host_barrier()
         if rank == 0:
             try:
                 files = e2e_from_files(args, world)
             except Exception as e:  # reported, never allowed to sink the bench line
                 files = {"error": str(e)}
-        R.barrier()
+        R.host_barrier()
 
     if rank == 0:
         clocks = m["clocks"]

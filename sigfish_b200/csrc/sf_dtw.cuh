@@ -819,29 +819,54 @@ __global__ void sf_verify_kernel(const sf_verify_args a)
 }
 
 // Splits the reads of a batch into those with exactly q_full events (pair kernel; flagged with status bit 5)
-// and the rest (warp-per-read kernel), both in ascending read order.  One warp.
-__global__ void sf_partition_kernel(sf_readinfo *info, int n_reads, int q_full, int32_t *list_full, int32_t *list_other,
-                                    int32_t *counts)
+// and the rest (warp-per-read kernel), both in ascending read order.  One block of SF_PART_THREADS threads.
+#define SF_PART_THREADS 1024
+__global__ void __launch_bounds__(SF_PART_THREADS) sf_partition_kernel(sf_readinfo *info, int n_reads, int q_full, int32_t *list_full,
+                                                                        int32_t *list_other, int32_t *counts)
 {
-    const int lane = threadIdx.x;
-    int nf = 0, no = 0;
-    for (int base = 0; base < n_reads; base += 32) {
-        const int i = base + lane;
+    __shared__ int wf[SF_PART_THREADS / 32], wo[SF_PART_THREADS / 32];
+    __shared__ int base_f, base_o;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        base_f = 0;
+        base_o = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_reads; base += SF_PART_THREADS) {
+        const int i = base + tid;
         const int ql = i < n_reads ? info[i].qlen : -1;
         const bool isf = ql == q_full, iso = ql > 0 && !isf;
         const unsigned mf = __ballot_sync(0xffffffffu, isf), mo = __ballot_sync(0xffffffffu, iso);
+        if (lane == 0) {
+            wf[warp] = __popc(mf);
+            wo[warp] = __popc(mo);
+        }
+        __syncthreads();
+        int pf = base_f, po = base_o, tf = 0, to = 0;
+        for (int w = 0; w < SF_PART_THREADS / 32; w++) {
+            if (w < warp) {
+                pf += wf[w];
+                po += wo[w];
+            }
+            tf += wf[w];
+            to += wo[w];
+        }
         const unsigned below = (1u << lane) - 1u;
         if (isf) {
-            list_full[nf + __popc(mf & below)] = i;
+            list_full[pf + __popc(mf & below)] = i;
             info[i].status |= 32;
         }
         if (iso)
-            list_other[no + __popc(mo & below)] = i;
-        nf += __popc(mf);
-        no += __popc(mo);
+            list_other[po + __popc(mo & below)] = i;
+        __syncthreads();
+        if (tid == 0) {
+            base_f += tf;
+            base_o += to;
+        }
+        __syncthreads();
     }
-    if (lane == 0) {
-        counts[0] = nf;
-        counts[1] = no;
+    if (tid == 0) {
+        counts[0] = base_f;
+        counts[1] = base_o;
     }
 }

@@ -16,7 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfgpu.h"
@@ -304,17 +306,19 @@ template <int RQ, bool STD> cudaError_t launch_pair(const sf_dtw_args &a, int gr
     return cudaLaunchKernelEx(&cfg, sf_dtw_pair_kernel<16, STD, RQ, false>, a);
 }
 
-// the pair kernel is instantiated for the query sizes 250 (last row in register 9 of its lane) and 256 (15)
+// the pair kernel is instantiated for every register the last query row can sit in (RQ = (q - 1) % 16), i.e. for
+// every query size in (128, 256]
+template <typename F, int... RQs> bool dispatch_pair(int rq, bool std_dtw, F &&f, std::integer_sequence<int, RQs...>)
+{
+    return ((rq == RQs && (std_dtw ? (f(std::integral_constant<int, RQs>{}, std::true_type{}), true)
+                                   : (f(std::integral_constant<int, RQs>{}, std::false_type{}), true))) || ...);
+}
 #define SF_DISPATCH_PAIR(RQ_, STD_, EXPR)                                                         \
-    do {                                                                                          \
-        if ((RQ_) == 9) {                                                                         \
-            constexpr int RQ = 9;                                                                 \
-            if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } \
-        } else {                                                                                  \
-            constexpr int RQ = 15;                                                                \
-            if (STD_) { constexpr bool STD = true; EXPR; } else { constexpr bool STD = false; EXPR; } \
-        }                                                                                         \
-    } while (0)
+    dispatch_pair((RQ_), (STD_), [&](auto rq_tag_, auto std_tag_) {                               \
+        constexpr int RQ = decltype(rq_tag_)::value;                                              \
+        constexpr bool STD = decltype(std_tag_)::value;                                           \
+        EXPR;                                                                                     \
+    }, std::make_integer_sequence<int, 16>{})
 
 template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaStream_t st)
 {
@@ -328,7 +332,7 @@ template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cuda
 {
     const int warps = 4;
     const int grid = (a.n_reads + warps - 1) / warps;
-    if constexpr (R == 8) { // pairing exists for q = 250 / 256 only, i.e. R = 8 in the warp-per-read layout
+    if constexpr (R >= 5 && R <= 8) { // pairing exists for 128 < q <= 256, i.e. R = 5..8 in the warp-per-read layout
         if (pair) {
             // the reads the pair kernel aligned are traced two per warp; the others by the general kernel
             sf_trace_kernel<R, STD, 16><<<grid, warps * 32, 0, st>>>(a);
@@ -481,7 +485,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             // is launched with programmatic stream serialisation, so it starts then instead of after the end.
             // Blocks of the first kernel that find the queue empty exit at once and leave their place to pair
             // blocks: a few ragged reads in a batch cost no extra wave.
-            sf_partition_kernel<<<1, 32, 0, st>>>(s.d_info, n, c->opt.query_size, s.d_list_full, s.d_list_other, s.d_counts);
+            sf_partition_kernel<<<1, SF_PART_THREADS, 0, st>>>(s.d_info, n, c->opt.query_size, s.d_list_full, s.d_list_other, s.d_counts);
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
             oa.list = s.d_list_other;
@@ -919,17 +923,44 @@ int submit_common(sfgpu_ctx *c, int32_t slot, int32_t n_reads, PtrFn ptr, LenFn 
         const int64_t len = len_of(i);
         s.h_off[i] = cur;
         h_len[i] = len;
-        if (len > 0)
-            memcpy(s.h_signal + cur, ptr(i), sizeof(int16_t) * (size_t)len);
-        const int64_t end = cur + ((len + 7) & ~7ll);
-        for (int64_t j = cur + len; j < end; j++)
-            s.h_signal[j] = 0;
-        cur = end;
+        cur += (len + 7) & ~7ll;
         s.h_scal[i] = digitisation[i];
         s.h_scal[s.cap_reads + i] = offset[i];
         s.h_scal[2 * (size_t)s.cap_reads + i] = range[i];
     }
     s.h_off[n_reads] = cur;
+    // gather of the samples into the pinned staging buffer: the only per-sample work of the host on this path.  One
+    // core copies ~8 GB/s, which is less than a batch of short-reference work needs (65 k reads, 590 MB, against
+    // 140 ms of device time), so large batches are copied by a few threads.
+    auto copy_range = [&](int b, int e) {
+        for (int i = b; i < e; i++) {
+            const int64_t len = h_len[i], at = s.h_off[i];
+            if (len > 0)
+                memcpy(s.h_signal + at, ptr(i), sizeof(int16_t) * (size_t)len);
+            for (int64_t j = at + len; j < s.h_off[i + 1]; j++)
+                s.h_signal[j] = 0;
+        }
+    };
+    const int n_thr = (int)std::min<int64_t>(std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2)),
+                                             cur / (8 << 20));
+    if (n_thr <= 1) {
+        copy_range(0, n_reads);
+    } else {
+        std::vector<std::thread> th;
+        int b = 0;
+        for (int t = 0; t < n_thr; t++) { // ranges of about equal sample counts
+            const int64_t upto = cur * (t + 1) / n_thr;
+            int e = b;
+            while (e < n_reads && s.h_off[e + 1] <= upto)
+                e++;
+            if (t + 1 == n_thr)
+                e = n_reads;
+            th.emplace_back(copy_range, b, e);
+            b = e;
+        }
+        for (auto &t : th)
+            t.join();
+    }
     s.n_reads = n_reads;
     s.n_samples = cur;
     s.raw_samples = raw;
@@ -1036,8 +1067,10 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             return fail(c, SFGPU_ECUDA, "DTW kernel does not fit on the device (R=%d)", rows);
         c->dtw_blocks_per_sm = nb;
         c->ck_floats = sf_ckpt_floats(rows);
-        // two full-length reads per warp for the query sizes the pair kernel is built for (reserved[3] = 1: off)
-        if ((opt->query_size == 250 || opt->query_size == 256) && opt->reserved[3] == 0) {
+        // two full-length reads per warp (16 lanes x 16 rows each) whenever a query fills more than half of the 16
+        // lanes, i.e. 128 < q <= 256; shorter queries keep one read per warp with fewer rows per lane
+        // (reserved[3] = 1: pairing off)
+        if (opt->query_size > 128 && opt->query_size <= 256 && opt->reserved[3] == 0) {
             c->R2 = 16;
             c->RQ2 = (opt->query_size - 1) % 16;
             c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);

@@ -182,7 +182,45 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
     }
 
     SF_STAGE("model read");
-    /* GPUs */
+    /* GPUs.  Initialising the CUDA driver costs about 0.6 s per visible GPU on a B200 box (measured:
+     * tools/gpuinit_probe.cu, profiles/r02_cli_trace_*), whether the GPU is used or not, so when the user asked for
+     * fewer GPUs than the box has, only those are made visible before the first CUDA call. */
+    if (opt.num_gpus > 0) {
+        const int first_req = opt.first_gpu > 0 ? opt.first_gpu : 0;
+        const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+        char list[1024];
+        size_t len = 0;
+        int ok = 1;
+        if (vis && *vis) { /* entries [first, first + n) of the list that is already in force */
+            const char *p = vis;
+            int idx = 0, taken = 0;
+            while (*p && taken < opt.num_gpus) {
+                const char *e = strchr(p, ',');
+                const size_t l = e ? (size_t)(e - p) : strlen(p);
+                if (idx >= first_req) {
+                    if (len + l + 2 > sizeof list) { ok = 0; break; }
+                    if (taken) list[len++] = ',';
+                    memcpy(list + len, p, l);
+                    len += l;
+                    taken++;
+                }
+                idx++;
+                if (!e) break;
+                p = e + 1;
+            }
+            if (taken < opt.num_gpus) ok = 0; /* fewer entries than asked for: let the check below report it */
+        } else {
+            for (int g = 0; g < opt.num_gpus && ok; g++) {
+                const int w = snprintf(list + len, sizeof list - len, "%s%d", g ? "," : "", first_req + g);
+                if (w < 0 || (size_t)w >= sizeof list - len) ok = 0; else len += (size_t)w;
+            }
+        }
+        if (ok && len > 0) {
+            list[len] = 0;
+            setenv("CUDA_VISIBLE_DEVICES", list, 1);
+            opt.first_gpu = 0;
+        }
+    }
     int ndev = sfgpu_device_count();
     SF_STAGE("device count");
     if (ndev < 1) {

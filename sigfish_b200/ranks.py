@@ -29,6 +29,7 @@ class Ranks:
         self.rank, self.world, self.local = env_rank()
         self.device = device if device is not None else torch.device("cpu")
         self.owned = False
+        self._gloo = None
         if self.world > 1 and not dist.is_initialized():
             kw = {}
             if backend == "nccl":
@@ -41,6 +42,15 @@ class Ranks:
             self.dist.barrier()
         if self.device.type == "cuda":
             self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """barrier that waits on the CPU (a gloo group).  Ranks idling in an NCCL barrier keep a kernel spinning on
+        their GPU; a process that uses that GPU meanwhile (bench.py's from-files run of the command line on all
+        GPUs) is then time-sliced against it and runs at half speed (measured)."""
+        if self.world > 1:
+            if self._gloo is None:
+                self._gloo = self.dist.new_group(backend="gloo")
+            self.dist.barrier(group=self._gloo)
 
     def _reduce(self, values, op):
         t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)

@@ -234,7 +234,7 @@ def test_dtw_kernel_matches_oracle_random_and_ties(q, quant):
     oref.close()
 
 
-@pytest.mark.parametrize("q", [100, 250, 256, 300, 500])
+@pytest.mark.parametrize("q", [100, 180, 250, 256, 300, 500])
 @pytest.mark.parametrize("quant", [0, 2])
 @pytest.mark.parametrize("warm", [0, 1])
 def test_split_segments_match_oracle(q, quant, warm):
@@ -729,10 +729,14 @@ def test_slow_and_fast_reads_in_one_batch():
     ctx.close()
 
 
-@pytest.mark.parametrize("q", [250, 256])
-@pytest.mark.parametrize("std", [False, True])
+# query sizes in (128, 256] that put the last query row in register 0, 1, ... 15 of its lane: one per instantiation
+# of the pair kernel
+_PAIR_Q = [129, 146, 163, 180, 197, 214, 231, 248, 137, 250, 155, 172, 189, 206, 223, 256]
+
+
+@pytest.mark.parametrize("q,std", [(q, False) for q in _PAIR_Q] + [(q, True) for q in (197, 250, 256)])
 def test_paired_and_unpaired_layouts_agree(q, std):
-    """q = 250 / 256: full-length reads run two per warp (sf_dtw_pair_kernel), the others one per warp.  Both
+    """128 < q <= 256: full-length reads run two per warp (sf_dtw_pair_kernel), the others one per warp.  Both
     layouts must give the oracle's answer and identical bytes; odd and even counts of full-length reads,
     ragged reads mixed in, checkpoints on (restart from half-warp checkpoints) and off"""
     rng = np.random.default_rng(5 * q + std)

@@ -58,6 +58,7 @@ def _worker(rank, world, port, q):
         h = H.orc_map(ref, sigs[i], 8192.0, 10.0, 1402.882, 0, 250, 50)
         rows.append((i, h.rid, h.strand.decode(), h.pos_st, h.pos_end, float(h.score)))
     R.barrier()
+    R.host_barrier()  # the CPU-side barrier bench.py uses around its from-files stage
     mx = R.max([10.0 + R.rank, 3.0])
     sm = R.sum([float(e - b), 250.0 * (e - b)])
     allrows = R.gather_ordered(rows)
