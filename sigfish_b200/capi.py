@@ -110,7 +110,8 @@ class Context:
         self.opt.reserved[0] = ck_min_cols  # test knob: checkpoint segments longer than this
         self.opt.reserved[1] = min_window   # test knob: restart distance of the start-coordinate pass
         self.opt.reserved[2] = warm_blocks  # test knob: warm-up of a piece of a split segment, in 64-column blocks
-        self.opt.reserved[3] = int(no_pairing)  # test knob: one read per warp even for q = 250 / 256
+        # test knob: True = one read per warp even where pairing is the default, 2 = pair for every 128 < q <= 256
+        self.opt.reserved[3] = int(no_pairing)
         self.opt.reserved[4] = piece_periods  # test knob: piece length in checkpoint periods (< 0: never split)
         lm = np.ascontiguousarray(level_mean, dtype=np.float32)
         assert lm.shape[0] == 4 ** kmer_size

@@ -267,13 +267,21 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
 
         // ---- 4: sequential peak finders + event closing (lane 0) ----
         if (tid == 0) {
+            // the two statistics of the next position are fetched one iteration ahead: the loads do not depend on the
+            // detector state, their latency would otherwise sit in every step of the serial chain
+            float nx1 = T1[0], nx2 = T2[0];
             for (long long i = lo_pos; i < hi_pos; i++) {
+                const float cur1 = nx1, cur2 = nx2;
+                if (i + 1 < hi_pos) {
+                    nx1 = T1[i + 1 - lo_pos];
+                    nx2 = T2[i + 1 - lo_pos];
+                }
 #pragma unroll
                 for (int d = 0; d < 2; d++) {
                     sf_finder &me = d == 0 ? f0 : f1;
                     if (me.masked_to >= (unsigned long long)i)
                         continue;
-                    const float v = d == 0 ? T1[i - lo_pos] : T2[i - lo_pos];
+                    const float v = d == 0 ? cur1 : cur2;
                     if (me.peak_pos < 0) {
                         if (v < me.peak_val) {
                             me.peak_val = v;
@@ -348,9 +356,11 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         __syncwarp();
     }
 
-    // ---- window + z-score + query (thread 0; fp32 sums in the reference's order) ----
+    // ---- window + z-score + query (fp32 sums in the reference's order by lane 0; everything elementwise by the warp) ----
+    sf_readinfo ri;
+    ri.status = 0; ri.n_events = 0; ri.qstart = ri.qend = ri.qlen = 0; ri.start_raw = ri.end_raw = 0;
+    long long lo = 0, hi = 0;
     if (tid == 0) {
-        sf_readinfo ri;
         ri.status = sticky ? 8 : 0;
         long long nev;
         if (stop_flag) {
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
             nev = npk + 1;
         }
         ri.n_events = nev;
-        long long lo = 0, hi = 0, nn = nev;
+        long long nn = nev;
         if (nn > 0) {
             if (!from_end) { // sigfish.c:435-462
                 lo = a.p;
@@ -402,41 +412,69 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         int qlen = nn > 0 ? (int)(hi - lo) : 0;
         if (qlen > a.q_cap) qlen = 0; // cannot happen (hi - lo <= q)
         ri.qlen = qlen;
-        ri.start_raw = 0; ri.end_raw = 0;
-        if (qlen > 0) {
-            // where event j of the window lives: ring slot, or in automatic mode the detected-start area
-            const long long base_q = (autop && qs >= 0) ? (long long)a.cap_a - qs : 0;
-            const bool ring = !autop;
+    }
+    // the window's events are read back by the whole warp (the stores above came from lane 0)
+    __syncwarp();
+    lo = __shfl_sync(full, lo, 0);
+    hi = __shfl_sync(full, hi, 0);
+    qs = __shfl_sync(full, qs, 0);
+    const int qlen = __shfl_sync(full, ri.qlen, 0);
+    if (qlen > 0) {
+        // where event j of the window lives: ring slot, or in automatic mode the detected-start area
+        const long long base_q = (autop && qs >= 0) ? (long long)a.cap_a - qs : 0;
+        const bool ring = !autop;
 #define SF_EV_SLOT(j) (ring ? (j) % cap : (j) + base_q)
-            // sigfish.c:483-502
+        // the prefix-sum buffers are free now: the window's event means are staged there (2 x 642 floats, enough for
+        // the largest query), so that the serial sums below run from shared memory
+        float *wm1 = reinterpret_cast<float *>(S), *wm2 = reinterpret_cast<float *>(SS);
+        const int half_cap = 2 * (SF_EV_KEEP + SF_EV_TILE + 1);
+        const bool staged = qlen <= 2 * half_cap;
+        if (staged) {
+            for (int k = tid; k < qlen; k += 32) {
+                const float m = ev_mean[SF_EV_SLOT(lo + k)];
+                if (k < half_cap) wm1[k] = m; else wm2[k - half_cap] = m;
+            }
+        }
+        __syncwarp();
+        auto mean_at = [&](int k) -> float {
+            if (staged)
+                return k < half_cap ? wm1[k] : wm2[k - half_cap];
+            return ev_mean[SF_EV_SLOT(lo + k)];
+        };
+        // sigfish.c:483-502: sequential fp32 sums
+        float mean = 0.0f, sd = 0.0f;
+        if (tid == 0) {
             const float cnt = (float)qlen;
-            float mean = 0.0f;
-            for (long long j = lo; j < hi; j++) mean = __fadd_rn(mean, ev_mean[SF_EV_SLOT(j)]);
+            for (int k = 0; k < qlen; k++) mean = __fadd_rn(mean, mean_at(k));
             mean = __fdiv_rn(mean, cnt);
             float var = 0.0f;
-            for (long long j = lo; j < hi; j++) {
-                const float d = __fsub_rn(ev_mean[SF_EV_SLOT(j)], mean);
+            for (int k = 0; k < qlen; k++) {
+                const float d = __fsub_rn(mean_at(k), mean);
                 var = __fadd_rn(var, __fmul_rn(d, d));
             }
             var = __fdiv_rn(var, cnt);
-            const float sd = __fsqrt_rn(var);
-            float *qv = a.queries + (size_t)read * a.q_cap;
-            const bool flip = rna && !(a.flags & SF_INV); // sigfish.c:857-867
-            for (long long j = lo; j < hi; j++) {
-                const float z = __fdiv_rn(__fsub_rn(ev_mean[SF_EV_SLOT(j)], mean), sd);
-                const int k = (int)(j - lo);
-                qv[flip ? qlen - 1 - k : k] = z;
-                if (a.win_start) {
-                    a.win_start[(size_t)read * a.q_cap + k] = ev_start[SF_EV_SLOT(j)];
-                    a.win_len[(size_t)read * a.q_cap + k] = ev_len[SF_EV_SLOT(j)];
-                }
+            sd = __fsqrt_rn(var);
+        }
+        mean = __shfl_sync(full, mean, 0);
+        sd = __shfl_sync(full, sd, 0);
+        float *qv = a.queries + (size_t)read * a.q_cap;
+        const bool flip = rna && !(a.flags & SF_INV); // sigfish.c:857-867
+        for (int k = tid; k < qlen; k += 32) {
+            const float z = __fdiv_rn(__fsub_rn(mean_at(k), mean), sd);
+            qv[flip ? qlen - 1 - k : k] = z;
+            if (a.win_start) {
+                a.win_start[(size_t)read * a.q_cap + k] = ev_start[SF_EV_SLOT(lo + k)];
+                a.win_len[(size_t)read * a.q_cap + k] = ev_len[SF_EV_SLOT(lo + k)];
             }
+        }
+        if (tid == 0) {
             // sigfish.c:804-805 (uint64 + float evaluates in fp32)
             ri.start_raw = ev_start[SF_EV_SLOT(lo)];
             const long long le = hi - 1;
             ri.end_raw = (uint64_t)__fadd_rn((float)ev_start[SF_EV_SLOT(le)], ev_len[SF_EV_SLOT(le)]);
-#undef SF_EV_SLOT
         }
-        a.info[read] = ri;
+#undef SF_EV_SLOT
     }
+    if (tid == 0)
+        a.info[read] = ri;
 }

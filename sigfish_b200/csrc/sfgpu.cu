@@ -902,9 +902,11 @@ int submit_common(sfgpu_ctx *c, int32_t slot, int32_t n_reads, PtrFn ptr, LenFn 
         return fail(c, SFGPU_EARG, "null batch array");
     SF_CUDA(c, cudaSetDevice(c->opt.device));
     sf_slot &s = c->slots[slot];
+    g_trace(c->opt.device, "submit: begin");
     int rc = slot_wait(c, s);
     if (rc)
         return rc;
+    g_trace(c->opt.device, "submit: slot free");
     // every read starts on a 16-byte boundary so that the event kernel can use 16-byte loads
     int64_t padded = 0, raw = 0;
     for (int i = 0; i < n_reads; i++) {
@@ -965,7 +967,10 @@ int submit_common(sfgpu_ctx *c, int32_t slot, int32_t n_reads, PtrFn ptr, LenFn 
     s.n_samples = cur;
     s.raw_samples = raw;
     s.queries_only = false;
-    return run_stages(c, s, true);
+    g_trace(c->opt.device, "submit: samples staged in pinned memory");
+    rc = run_stages(c, s, true);
+    g_trace(c->opt.device, "submit: stages enqueued");
+    return rc;
 }
 
 
@@ -1067,10 +1072,13 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             return fail(c, SFGPU_ECUDA, "DTW kernel does not fit on the device (R=%d)", rows);
         c->dtw_blocks_per_sm = nb;
         c->ck_floats = sf_ckpt_floats(rows);
-        // two full-length reads per warp (16 lanes x 16 rows each) whenever a query fills more than half of the 16
-        // lanes, i.e. 128 < q <= 256; shorter queries keep one read per warp with fewer rows per lane
-        // (reserved[3] = 1: pairing off)
-        if (opt->query_size > 128 && opt->query_size <= 256 && opt->reserved[3] == 0) {
+        // Two full-length reads per warp (16 lanes x 16 rows each) where that beats one read per warp: the pair layout
+        // computes 256 rows per read whatever q is, so its useful rate falls as q/256 (measured on the 1 Mb shape:
+        // q = 256 8.68, 250 8.37, 200 6.62, 130 4.22 TCUPS), while one read per warp pads only up to the next
+        // multiple of 32 rows at ~7 TCUPS.  The pair layout wins for 192 < q <= 256 (reserved[3]: 1 = pairing off,
+        // 2 = pairing for every 128 < q <= 256, used by the tests to reach every instantiation).
+        const int pair_from = opt->reserved[3] == 2 ? 128 : 192;
+        if (opt->query_size > pair_from && opt->query_size <= 256 && opt->reserved[3] != 1) {
             c->R2 = 16;
             c->RQ2 = (opt->query_size - 1) % 16;
             c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);
@@ -1355,9 +1363,11 @@ int sfgpu_collect(sfgpu_ctx *c, int32_t slot, sfgpu_result_t *out)
     sf_slot &s = c->slots[slot];
     if (!s.busy && !s.done)
         return fail(c, SFGPU_ESTATE, "sfgpu_collect: nothing was submitted to slot %d", slot);
+    g_trace(c->opt.device, "collect: begin");
     int rc = slot_wait(c, s);
     if (rc)
         return rc;
+    g_trace(c->opt.device, "collect: batch done");
     if (!out && s.n_reads > 0)
         return fail(c, SFGPU_EARG, "null result array");
     for (int i = 0; i < s.n_reads; i++) {
