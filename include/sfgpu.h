@@ -41,6 +41,7 @@ extern "C" {
 #define SFGPU_ENODEV (-3)  /* no usable sm_100 device */
 #define SFGPU_ESTATE (-4)  /* call out of order (e.g. submit before set_ref) */
 #define SFGPU_ELIMIT (-5)  /* unsupported size (e.g. query_size > 1024) */
+#define SFGPU_EDECODE (-6) /* a BLOW5 record could not be decoded on the device: decode the batch on the host and resubmit */
 
 typedef struct sfgpu_ctx sfgpu_ctx;
 
@@ -118,6 +119,20 @@ int sfgpu_submit_reads(sfgpu_ctx *ctx, int32_t slot, int32_t n_reads, const int1
                        const int64_t *n_samples, const float *digitisation, const float *offset,
                        const float *range);
 
+/* sfgpu_submit_reads for reads that are still BLOW5 records as they lie in the file: replaces, on top of what
+ * sfgpu_submit replaces, work_db(parse_single) = slow5_rec_depress_parse() (src/sigfish.c:317-328,1024; slow5lib
+ * src/slow5.c:2575-2609,3191-3283; src/slow5_press.c:1085-1133).  records[i] points at record_bytes[i] bytes (what
+ * follows the u64 size in the file); record_press / signal_press are the file header's methods (0 none, 1 zlib;
+ * 0 none, 1 svb-zd; anything else: SFGPU_ELIMIT).  The caller has read the head of each record: sig_pos[i] is the
+ * offset of the raw_signal field in the decompressed record (2 + id length + 4 + 32 + 8), sig_bytes[i] its size in
+ * bytes (the len_raw_signal field of an svb-zd file, 2 * samples otherwise), n_samples[i] the sample count.
+ * Inflate and signal decoding run on the device; sfgpu_collect() returns SFGPU_EDECODE when a record turns out
+ * malformed (the host then decodes the batch itself and resubmits it with sfgpu_submit_reads). */
+int sfgpu_submit_records(sfgpu_ctx *ctx, int32_t slot, int32_t n_reads, const uint8_t *const *records,
+                         const int64_t *record_bytes, int32_t record_press, int32_t signal_press, const int32_t *sig_pos,
+                         const int64_t *sig_bytes, const int64_t *n_samples, const float *digitisation, const float *offset,
+                         const float *range);
+
 /* Same as sfgpu_submit but re-runs the device stages on the inputs already resident in the slot
  * (no host->device copy).  Used to measure device-only throughput. */
 int sfgpu_resubmit(sfgpu_ctx *ctx, int32_t slot);
@@ -156,6 +171,10 @@ int sfgpu_ref_events(sfgpu_ctx *ctx, int32_t rid, int32_t strand, float *out, in
 int64_t sfgpu_event_table(sfgpu_ctx *ctx, const int16_t *signal, int64_t n_samples, float digitisation,
                           float offset, float range, uint64_t *start, float *length, float *mean,
                           int64_t cap);
+
+/* the int16 samples of read i of the slot's last batch as the device holds them (after sfgpu_submit_records: as
+ * the device decoded them); returns the sample count or < 0 */
+int64_t sfgpu_slot_signal(sfgpu_ctx *ctx, int32_t slot, int32_t read, int16_t *out, int64_t cap);
 
 /* the normalised query of read i of the slot's last batch (src/sigfish.c:857-867); returns qlen */
 int sfgpu_query(sfgpu_ctx *ctx, int32_t slot, int32_t read, float *out, int32_t cap);

@@ -19,7 +19,7 @@ SYMBOLS = ["sfgpu_device_count", "sfgpu_create", "sfgpu_set_ref", "sfgpu_submit"
            "sfgpu_collect", "sfgpu_timing", "sfgpu_destroy", "sfgpu_strerror", "sfgpu_ref_events",
            "sfgpu_event_table", "sfgpu_query", "sfgpu_ref_columns", "sfgpu_set_ref_events",
            "sfgpu_submit_queries", "sfgpu_collect_paths", "sfgpu_wave_reads",
-           "sfgpu_submit_reads"]
+           "sfgpu_submit_reads", "sfgpu_submit_records", "sfgpu_slot_signal"]
 
 
 class Opt(C.Structure):
@@ -66,6 +66,9 @@ def lib():
     L.sfgpu_set_ref.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_submit.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     L.sfgpu_submit_reads.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    L.sfgpu_submit_records.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.sfgpu_slot_signal.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64]
+    L.sfgpu_slot_signal.restype = C.c_int64
     L.sfgpu_resubmit.argtypes = [vp, C.c_int32]
     L.sfgpu_collect.argtypes = [vp, C.c_int32, vp]
     L.sfgpu_timing.argtypes = [vp, C.c_int32, C.POINTER(Timing)]
@@ -202,6 +205,28 @@ class Context:
         self._check(lib().sfgpu_submit_reads(self._h, slot, n, ptrs, _ptr(lens), _ptr(dig), _ptr(offs), _ptr(rng)),
                     "sfgpu_submit_reads")
         self._n[slot] = n
+
+    def submit_records(self, slot, records, record_press, signal_press, sig_pos, sig_bytes, n_samples, scalings):
+        """BLOW5 records as they lie in the file (list of bytes objects): inflate + signal decoding on the device"""
+        n = len(records)
+        keep = [np.frombuffer(r, dtype=np.uint8) if len(r) else np.zeros(0, np.uint8) for r in records]
+        ptrs = (C.c_void_p * max(n, 1))(*[(k.ctypes.data if k.size else 0) for k in keep])
+        nbytes = np.array([k.size for k in keep] or [0], dtype=np.int64)
+        spos = np.array(list(sig_pos) or [0], dtype=np.int32)
+        sbytes = np.array(list(sig_bytes) or [0], dtype=np.int64)
+        ns = np.array(list(n_samples) or [0], dtype=np.int64)
+        dig = np.array([sc["digitisation"] for sc in scalings] or [0], dtype=np.float32)
+        offs = np.array([sc["offset"] for sc in scalings] or [0], dtype=np.float32)
+        rng = np.array([sc["range"] for sc in scalings] or [0], dtype=np.float32)
+        self._check(lib().sfgpu_submit_records(self._h, slot, n, ptrs, _ptr(nbytes), int(record_press), int(signal_press),
+                                               _ptr(spos), _ptr(sbytes), _ptr(ns), _ptr(dig), _ptr(offs), _ptr(rng)),
+                    "sfgpu_submit_records")
+        self._n[slot] = n
+
+    def slot_signal(self, slot, read, n_samples) -> np.ndarray:
+        out = np.zeros(max(int(n_samples), 1), dtype=np.int16)
+        n = self._check(lib().sfgpu_slot_signal(self._h, slot, read, _ptr(out), out.shape[0]), "sfgpu_slot_signal")
+        return out[:n]
 
     def resubmit(self, slot):
         self._check(lib().sfgpu_resubmit(self._h, slot), "sfgpu_resubmit")

@@ -25,6 +25,7 @@
 #include "sf_types.cuh"
 #include "sf_events.cuh"
 #include "sf_qstart.cuh"
+#include "sf_blow5.cuh"
 #include "sf_ref.cuh"
 #include "sf_dtw.cuh"
 #include "sf_trace.cuh"
@@ -80,6 +81,15 @@ struct sf_slot {
     unsigned int *d_counter = nullptr;  // [4] task queues of the two DTW kernels and of their redo passes
     int32_t *d_list_full = nullptr, *d_list_other = nullptr, *d_counts = nullptr; // sf_partition_kernel; [2] = fronts that differed
     int32_t *h_counts = nullptr;        // pinned copy of d_counts
+    // records decoded on the device (sfgpu_submit_records): the compressed records, their inflated form, per-record
+    // layout (rec_off[n+1], rec_bytes[n], scr_off[n+1], sig_pos[n], sig_bytes[n]) and decode status
+    uint8_t *h_rec = nullptr, *d_rec = nullptr, *d_scratch = nullptr;
+    int64_t *h_rmeta = nullptr, *d_rmeta = nullptr;
+    int32_t *h_status = nullptr, *d_status = nullptr;
+    size_t cap_rec = 0, cap_scratch = 0, cap_rmeta = 0;
+    int64_t rec_total = 0;
+    bool records = false;
+    int32_t record_press = 0, signal_press = 0;
     // pieces of split segments: warm fronts, first differing piece per (read, split group); sized per batch
     float *d_warm = nullptr;
     int32_t *d_first_bad = nullptr;
@@ -192,6 +202,8 @@ void slot_free_buffers(sf_slot &s)
     dfree(s.d_ev_len); dfree(s.d_queries); dfree(s.d_info); dfree(s.d_res); dfree(s.d_ckpt);
     dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
     dfree(s.d_list_full); dfree(s.d_list_other); dfree(s.d_warm); dfree(s.d_first_bad);
+    hfree(s.h_rec); dfree(s.d_rec); dfree(s.d_scratch); hfree(s.h_rmeta); dfree(s.d_rmeta); hfree(s.h_status); dfree(s.d_status);
+    s.cap_rec = s.cap_scratch = s.cap_rmeta = 0;
     s.cap_reads = 0;
     s.cap_samples = 0;
     s.cap_res = s.cap_warm = s.cap_bad = 0;
@@ -380,13 +392,46 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         SF_CUDA(c, cudaMemcpyAsync(s.d_info, s.h_info, sizeof(sf_readinfo) * n, cudaMemcpyHostToDevice, st));
     }
     if (with_h2d && n > 0 && with_events) {
-        SF_CUDA(c, cudaMemcpyAsync(s.d_signal, s.h_signal, sizeof(int16_t) * s.n_samples, cudaMemcpyHostToDevice, st));
+        if (s.records) {
+            SF_CUDA(c, cudaMemcpyAsync(s.d_rec, s.h_rec, (size_t)s.rec_total, cudaMemcpyHostToDevice, st));
+            SF_CUDA(c, cudaMemcpyAsync(s.d_rmeta, s.h_rmeta, sizeof(int64_t) * (5 * (size_t)n + 2), cudaMemcpyHostToDevice, st));
+        } else {
+            SF_CUDA(c, cudaMemcpyAsync(s.d_signal, s.h_signal, sizeof(int16_t) * s.n_samples, cudaMemcpyHostToDevice, st));
+        }
         SF_CUDA(c, cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * (2 * (size_t)n + 1), cudaMemcpyHostToDevice, st));
         SF_CUDA(c, cudaMemcpyAsync(s.d_scal, s.h_scal, sizeof(float) * 3 * (size_t)s.cap_reads, cudaMemcpyHostToDevice, st));
     }
     SF_CUDA(c, cudaEventRecord(s.ev[1], st));
     s.timing.dtw_launches = 0;
     s.timing.other_launches = 0;
+    if (with_h2d && n > 0 && with_events && s.records) {
+        // BLOW5 records -> int16 samples on the device (sf_blow5.cuh); counted with the event stage
+        sf_rec_args ra;
+        ra.rec = s.d_rec;
+        ra.rec_off = s.d_rmeta;
+        ra.rec_bytes = s.d_rmeta + (n + 1);
+        ra.scr_off = s.d_rmeta + (2 * (size_t)n + 1);
+        ra.sig_pos = s.d_rmeta + (3 * (size_t)n + 2);
+        ra.sig_bytes = s.d_rmeta + (4 * (size_t)n + 2);
+        ra.scratch = s.d_scratch;
+        ra.sig_off = s.d_off;
+        ra.sig_len = s.d_off + (n + 1);
+        ra.signal = s.d_signal;
+        ra.n_reads = n;
+        ra.record_press = s.record_press;
+        ra.signal_press = s.signal_press;
+        ra.status = s.d_status;
+        SF_CUDA(c, cudaMemsetAsync(s.d_status, 0, sizeof(int32_t) * (size_t)n, st));
+        if (s.record_press) {
+            const int blocks = std::max(1, std::min((n + SF_INF_WARPS - 1) / SF_INF_WARPS, c->sm_count * 8));
+            sf_inflate_kernel<<<blocks, 32 * SF_INF_WARPS, SF_INF_WARPS * SF_INF_SMEM_WARP, st>>>(ra);
+            SF_CUDA(c, cudaGetLastError());
+            s.timing.other_launches++;
+        }
+        sf_signal_kernel<<<std::max(1, std::min((n + 3) / 4, c->sm_count * 16)), 128, 0, st>>>(ra);
+        SF_CUDA(c, cudaGetLastError());
+        s.timing.other_launches++;
+    }
     if (n > 0 && with_events) {
         sf_ev_args ea;
         ea.signal = s.d_signal;
@@ -577,6 +622,8 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         SF_CUDA(c, cudaMemcpyAsync(s.h_info, s.d_info, sizeof(sf_readinfo) * n, cudaMemcpyDeviceToHost, st));
         SF_CUDA(c, cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(sf_hit) * n, cudaMemcpyDeviceToHost, st));
         SF_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, st));
+        if (s.records && with_h2d)
+            SF_CUDA(c, cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
     SF_CUDA(c, cudaEventRecord(s.ev[5], st));
     s.busy = true;
@@ -967,6 +1014,7 @@ int submit_common(sfgpu_ctx *c, int32_t slot, int32_t n_reads, PtrFn ptr, LenFn 
     s.n_samples = cur;
     s.raw_samples = raw;
     s.queries_only = false;
+    s.records = false;
     g_trace(c->opt.device, "submit: samples staged in pinned memory");
     rc = run_stages(c, s, true);
     g_trace(c->opt.device, "submit: stages enqueued");
@@ -1294,6 +1342,134 @@ int sfgpu_submit_reads(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_
                          digitisation, offset, range);
 }
 
+int sfgpu_submit_records(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const uint8_t *const *records, const int64_t *record_bytes,
+                         int32_t record_press, int32_t signal_press, const int32_t *sig_pos, const int64_t *sig_bytes,
+                         const int64_t *n_samples, const float *digitisation, const float *offset, const float *range)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (!c->have_ref)
+        return fail(c, SFGPU_ESTATE, "sfgpu_submit_records before sfgpu_set_ref");
+    if (slot < 0 || slot >= (int)c->slots.size() || n_reads < 0)
+        return fail(c, SFGPU_EARG, "bad slot or read count");
+    if (n_reads > 0 && (!records || !record_bytes || !sig_pos || !sig_bytes || !n_samples || !digitisation || !offset || !range))
+        return fail(c, SFGPU_EARG, "null batch array");
+    if (record_press < 0 || record_press > 1 || signal_press < 0 || signal_press > 1)
+        return fail(c, SFGPU_ELIMIT, "record / signal compression %d / %d is not decoded on the device (zlib and svb-zd are)",
+                    record_press, signal_press);
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    g_trace(c->opt.device, "submit_records: begin");
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    // layout: records on 8-byte boundaries, inflated records with 256 bytes of slack (auxiliary fields behind the
+    // signal are inflated too so that the checksum can be verified), samples padded to multiples of 8
+    int64_t rec_total = 0, scr_total = 0, padded = 0, raw = 0;
+    for (int i = 0; i < n_reads; i++) {
+        const int64_t nb = record_bytes[i], ns = n_samples[i];
+        if (nb < 0 || ns < 0 || ns > 0x7fffff00ll || sig_pos[i] < 0 || sig_bytes[i] < 0 || (nb > 0 && !records[i]))
+            return fail(c, SFGPU_EARG, "bad record %d", i);
+        if (!record_press && (int64_t)sig_pos[i] + sig_bytes[i] > nb)
+            return fail(c, SFGPU_EARG, "record %d: signal field runs past the record", i);
+        rec_total += (nb + 7) & ~7ll;
+        if (record_press)
+            scr_total += ((int64_t)sig_pos[i] + sig_bytes[i] + 256 + 15) & ~15ll;
+        padded += (ns + 7) & ~7ll;
+        raw += ns;
+    }
+    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8);
+    if (rc)
+        return rc;
+    if ((size_t)rec_total + 16 > s.cap_rec) {
+        hfree(s.h_rec); dfree(s.d_rec);
+        s.cap_rec = 0;
+        const size_t cap = (size_t)rec_total + (size_t)rec_total / 4 + (1 << 20);
+        SF_CUDA(c, cudaMallocHost(&s.h_rec, cap));
+        SF_CUDA(c, cudaMalloc(&s.d_rec, cap));
+        s.cap_rec = cap;
+    }
+    if ((size_t)scr_total + 16 > s.cap_scratch) {
+        dfree(s.d_scratch);
+        s.cap_scratch = 0;
+        const size_t cap = (size_t)scr_total + (size_t)scr_total / 4 + (1 << 20);
+        SF_CUDA(c, cudaMalloc(&s.d_scratch, cap));
+        s.cap_scratch = cap;
+    }
+    if ((size_t)s.cap_reads > s.cap_rmeta) {
+        hfree(s.h_rmeta); dfree(s.d_rmeta); hfree(s.h_status); dfree(s.d_status);
+        s.cap_rmeta = 0;
+        const size_t n = (size_t)s.cap_reads;
+        SF_CUDA(c, cudaMallocHost(&s.h_rmeta, sizeof(int64_t) * (5 * n + 2)));
+        SF_CUDA(c, cudaMalloc(&s.d_rmeta, sizeof(int64_t) * (5 * n + 2)));
+        SF_CUDA(c, cudaMallocHost(&s.h_status, sizeof(int32_t) * n));
+        SF_CUDA(c, cudaMalloc(&s.d_status, sizeof(int32_t) * n));
+        s.cap_rmeta = n;
+    }
+    const size_t n = (size_t)n_reads;
+    int64_t *rec_off = s.h_rmeta, *rec_len = s.h_rmeta + (n + 1), *scr_off = s.h_rmeta + (2 * n + 1),
+            *spos = s.h_rmeta + (3 * n + 2), *sbytes = s.h_rmeta + (4 * n + 2);
+    int64_t *h_len = s.h_off + (n_reads + 1);
+    int64_t rcur = 0, scur = 0, cur = 0;
+    for (int i = 0; i < n_reads; i++) {
+        rec_off[i] = rcur;
+        rec_len[i] = record_bytes[i];
+        scr_off[i] = scur;
+        spos[i] = sig_pos[i];
+        sbytes[i] = sig_bytes[i];
+        s.h_off[i] = cur;
+        h_len[i] = n_samples[i];
+        rcur += (record_bytes[i] + 7) & ~7ll;
+        if (record_press)
+            scur += ((int64_t)sig_pos[i] + sig_bytes[i] + 256 + 15) & ~15ll;
+        cur += (n_samples[i] + 7) & ~7ll;
+        s.h_scal[i] = digitisation[i];
+        s.h_scal[s.cap_reads + i] = offset[i];
+        s.h_scal[2 * (size_t)s.cap_reads + i] = range[i];
+    }
+    rec_off[n_reads] = rcur;
+    scr_off[n_reads] = scur;
+    s.h_off[n_reads] = cur;
+    for (int i = 0; i < n_reads; i++) { // the compressed bytes: the only per-record copy the host makes
+        if (record_bytes[i] > 0)
+            memcpy(s.h_rec + rec_off[i], records[i], (size_t)record_bytes[i]);
+        memset(s.h_rec + rec_off[i] + record_bytes[i], 0, (size_t)(rec_off[i + 1] - rec_off[i] - record_bytes[i]));
+    }
+    s.n_reads = n_reads;
+    s.n_samples = cur;
+    s.raw_samples = raw;
+    s.rec_total = rcur;
+    s.queries_only = false;
+    s.records = true;
+    s.record_press = record_press;
+    s.signal_press = signal_press;
+    g_trace(c->opt.device, "submit_records: records staged in pinned memory");
+    rc = run_stages(c, s, true);
+    g_trace(c->opt.device, "submit_records: stages enqueued");
+    return rc;
+}
+
+int64_t sfgpu_slot_signal(sfgpu_ctx *c, int32_t slot, int32_t read, int16_t *out, int64_t cap)
+{
+    if (!c)
+        return fail(nullptr, SFGPU_EARG, "null context");
+    if (slot < 0 || slot >= (int)c->slots.size())
+        return fail(c, SFGPU_EARG, "bad slot");
+    SF_CUDA(c, cudaSetDevice(c->opt.device));
+    sf_slot &s = c->slots[slot];
+    int rc = slot_wait(c, s);
+    if (rc)
+        return rc;
+    if (!s.done || s.queries_only || read < 0 || read >= s.n_reads)
+        return fail(c, SFGPU_EARG, "no such read in slot %d", slot);
+    const int64_t len = s.h_off[s.n_reads + 1 + read];
+    if (len > cap || (len > 0 && !out))
+        return fail(c, SFGPU_EARG, "buffer too small");
+    if (len > 0)
+        SF_CUDA(c, cudaMemcpy(out, s.d_signal + s.h_off[read], sizeof(int16_t) * (size_t)len, cudaMemcpyDeviceToHost));
+    return len;
+}
+
 int sfgpu_submit_queries(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const float *queries,
                          const int32_t *qlen)
 {
@@ -1334,6 +1510,7 @@ int sfgpu_submit_queries(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const floa
     s.n_samples = 0;
     s.raw_samples = 0;
     s.queries_only = true;
+    s.records = false;
     return run_stages(c, s, true, false);
 }
 
@@ -1370,6 +1547,10 @@ int sfgpu_collect(sfgpu_ctx *c, int32_t slot, sfgpu_result_t *out)
     g_trace(c->opt.device, "collect: batch done");
     if (!out && s.n_reads > 0)
         return fail(c, SFGPU_EARG, "null result array");
+    if (s.records)
+        for (int i = 0; i < s.n_reads; i++)
+            if (s.h_status[i] != 0)
+                return fail(c, SFGPU_EDECODE, "record %d of the batch could not be decoded on the device (status %d)", i, s.h_status[i]);
     for (int i = 0; i < s.n_reads; i++) {
         const sf_readinfo &ri = s.h_info[i];
         const sf_hit &h = s.h_hits[i];

@@ -47,6 +47,7 @@ static struct option long_options[] = {
     {"pore", required_argument, 0, 0},       /* 24 */
     {"gpus", required_argument, 0, 0},       /* 25 B200 */
     {"gpu-first", required_argument, 0, 0},  /* 26 B200 */
+    {"device-decode", required_argument, 0, 0}, /* 27 B200 */
     {0, 0, 0, 0}};
 
 static int64_t parse_num(const char *str)
@@ -86,6 +87,7 @@ static void print_help_msg(FILE *fp, const opt_t *opt)
     fprintf(fp, "   --pore STR                 set the pore chemistry (r9, r10 or rna004) [auto]\n");
     fprintf(fp, "   --gpus INT                 number of B200 GPUs to shard the reads over [all]\n");
     fprintf(fp, "   --gpu-first INT            ordinal of the first GPU to use [0]\n");
+    fprintf(fp, "   --device-decode=yes|no     inflate / svb-zd decode BLOW5 records on the GPUs instead of the host threads [yes]\n");
     fprintf(fp, "\nadvanced options:\n");
     fprintf(fp, "   --kmer-model FILE          nucleotide k-mer model file (required: no built-in models in this build)\n");
     fprintf(fp, "   --rna                      the dataset is direct RNA\n");
@@ -297,6 +299,13 @@ int dtw_main(int argc, char *argv[])
                 SF_FATAL("Number of GPUs should larger than 0. You entered %d", opt.num_gpus);
         } else if (c == 0 && longindex == 26) {
             opt.first_gpu = atoi(optarg);
+        } else if (c == 0 && longindex == 27) {
+            if (!strcmp(optarg, "yes") || !strcmp(optarg, "y"))
+                opt.device_decode = 1;
+            else if (!strcmp(optarg, "no") || !strcmp(optarg, "n"))
+                opt.device_decode = 0;
+            else
+                SF_FATAL("%s", "option '--device-decode' requires an argument 'yes' or 'no'");
         }
     }
 

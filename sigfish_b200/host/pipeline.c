@@ -56,6 +56,7 @@ void init_opt(opt_t *opt)
     opt->prefix_size = 50;
     opt->query_size = 250;
     opt->verbosity = 4;
+    opt->device_decode = 1;
 }
 
 /* src/sigfish.c:22-52 */
@@ -293,6 +294,9 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
 
     core->opt = opt;
     core->realtime0 = realtime0;
+    /* BLOW5 records go to the GPUs as they are (zlib / uncompressed records, svb-zd / uncompressed signals) */
+    core->device_decode = opt.device_decode && sf_s5_is_binary(core->sf) && sf_s5_record_press(core->sf) <= 1 &&
+                          sf_s5_signal_press(core->sf) <= 1;
     return core;
 }
 
@@ -327,6 +331,10 @@ db_t *init_db(core_t *core)
     db->res = (sfgpu_result_t *)calloc(n, sizeof(sfgpu_result_t));
     db->aln = (aln_t *)calloc(n, sizeof(aln_t));
     db->out = (char **)calloc(n, sizeof(char *));
+    db->mem_views = sf_s5_is_mapped(core->sf);
+    db->sig_pos = (int32_t *)calloc(n, sizeof(int32_t));
+    db->sig_bytes = (int64_t *)calloc(n, sizeof(int64_t));
+    db->rec_bytes = (int64_t *)calloc(n, sizeof(int64_t));
     db->sig_off = (int64_t *)calloc(n + 1, sizeof(int64_t));
     db->sig_ptr = (int16_t **)calloc(n, sizeof(int16_t *));
     db->dig = (float *)calloc(n, sizeof(float));
@@ -354,7 +362,14 @@ ret_status_t load_db(core_t *core, db_t *db)
     ret_status_t status = {0, 0};
     while (db->n_rec < db->capacity_rec && db->sum_bytes < core->opt.batch_size_bytes) {
         const int i = db->n_rec;
-        const int64_t got = sf_s5_get_next_mem(core->sf, &db->mem_records[i], &db->mem_cap[i]);
+        int64_t got;
+        if (db->mem_views) { /* mapped BLOW5: the record stays where it is in the page cache */
+            const char *view = NULL;
+            got = sf_s5_get_next_view(core->sf, &view);
+            db->mem_records[i] = (char *)view;
+        } else {
+            got = sf_s5_get_next_mem(core->sf, &db->mem_records[i], &db->mem_cap[i]);
+        }
         if (got < 0) {
             SF_FATAL("Error reading from SLOW5 file: %s", sf_s5_error(core->sf));
         }
@@ -379,6 +394,7 @@ typedef struct {
     char *scratch;
     size_t scratch_cap;
     int failed;
+    int heads_only;
 } parse_arg_t;
 
 static void *parse_worker(void *p)
@@ -388,6 +404,14 @@ static void *parse_worker(void *p)
         const int32_t i = __sync_fetch_and_add(a->next, 1);
         if (i >= a->db->n_rec)
             break;
+        if (a->heads_only) {
+            if (sf_s5_parse_head(a->core->sf, a->db->mem_records[i], a->db->mem_bytes[i], &a->db->rec[i], &a->db->sig_pos[i],
+                                 &a->db->sig_bytes[i], &a->scratch, &a->scratch_cap)) {
+                a->failed = i + 1; /* the whole batch is then decoded on the host */
+                break;
+            }
+            continue;
+        }
         if (sf_s5_parse(a->core->sf, a->db->mem_records[i], a->db->mem_bytes[i], &a->db->rec[i], &a->scratch,
                         &a->scratch_cap)) {
             a->failed = i + 1;
@@ -399,7 +423,9 @@ static void *parse_worker(void *p)
     return NULL;
 }
 
-void parse_db(core_t *core, db_t *db)
+/* heads_only: read id, scaling and sample count of every record, the device decodes the signals; a record whose
+ * head cannot be read that way sends the whole batch through the full host decoder */
+static int parse_db_mode(core_t *core, db_t *db, int heads_only)
 {
     const double t0 = sf_realtime();
     int nt = core->opt.num_thread < 1 ? 1 : core->opt.num_thread;
@@ -412,6 +438,7 @@ void parse_db(core_t *core, db_t *db)
         args[t].core = core;
         args[t].db = db;
         args[t].next = &next;
+        args[t].heads_only = heads_only;
     }
     if (nt == 1) {
         parse_worker(&args[0]);
@@ -423,13 +450,31 @@ void parse_db(core_t *core, db_t *db)
         for (int t = 0; t < nt; t++)
             pthread_join(tid[t], NULL);
     }
+    int failed = 0;
     for (int t = 0; t < nt; t++)
         if (args[t].failed) {
-            SF_FATAL("Error parsing the record %d of the batch", args[t].failed - 1);
+            if (!heads_only) {
+                SF_FATAL("Error parsing the record %d of the batch", args[t].failed - 1);
+            }
+            failed = 1;
         }
     free(args);
     free(tid);
     core->parse_time += sf_realtime() - t0;
+    return failed;
+}
+
+void parse_db(core_t *core, db_t *db)
+{
+    db->heads_only = 0;
+    if (core->device_decode && db->n_rec > 0) {
+        if (parse_db_mode(core, db, 1) == 0) {
+            db->heads_only = 1;
+            return;
+        }
+        core->decode_fallbacks++;
+    }
+    parse_db_mode(core, db, 0);
 }
 
 /* Splits n_rec reads into G contiguous ranges [begin[g], begin[g+1]) of about the same total weight (a
@@ -467,8 +512,15 @@ static void *gpu_submit_worker(void *p)
     gpu_submit_arg_t *a = (gpu_submit_arg_t *)p;
     db_t *db = a->db;
     const int b = db->shard_begin[a->g], e = db->shard_begin[a->g + 1];
-    if (sfgpu_submit_reads(a->core->gpu[a->g], db->slot, e - b, (const int16_t *const *)db->sig_ptr + b, db->sig_off + b,
-                           db->dig + b, db->off + b, db->rng + b) != SFGPU_OK)
+    int rc;
+    if (db->heads_only)
+        rc = sfgpu_submit_records(a->core->gpu[a->g], db->slot, e - b, (const uint8_t *const *)db->mem_records + b, db->rec_bytes + b,
+                                  sf_s5_record_press(a->core->sf), sf_s5_signal_press(a->core->sf), db->sig_pos + b,
+                                  db->sig_bytes + b, db->sig_off + b, db->dig + b, db->off + b, db->rng + b);
+    else
+        rc = sfgpu_submit_reads(a->core->gpu[a->g], db->slot, e - b, (const int16_t *const *)db->sig_ptr + b, db->sig_off + b,
+                                db->dig + b, db->off + b, db->rng + b);
+    if (rc != SFGPU_OK)
         a->failed = 1;
     return NULL;
 }
@@ -497,6 +549,7 @@ void submit_db(core_t *core, db_t *db)
     for (int i = 0; i < db->n_rec; i++) {
         const sf_rec_t *r = &db->rec[i];
         db->sig_ptr[i] = r->raw_signal;
+        db->rec_bytes[i] = (int64_t)db->mem_bytes[i];
         db->sig_off[i] = (int64_t)r->len_raw_signal; /* used as the length array here */
         /* narrowed to float exactly as event_single() does (src/sigfish.c:335-337) */
         db->dig[i] = (float)r->digitisation;
@@ -676,6 +729,29 @@ void collect_db(core_t *core, db_t *db)
 {
     if (!db->submitted)
         return;
+    if (db->heads_only) {
+        /* a record the device could not decode (malformed, or a stream its inflate rejects): the host decodes the
+         * batch with its own reader -- which reports what is wrong with the record -- and submits the samples */
+        int bad = 0;
+        for (int g = 0; g < core->num_gpus; g++) {
+            const int rc = sfgpu_collect(core->gpu[g], db->slot, db->res + db->shard_begin[g]);
+            if (rc == SFGPU_EDECODE) {
+                SF_WARNING("GPU %d: %s; decoding this batch on the host", g, sfgpu_strerror(core->gpu[g]));
+                bad = 1;
+            } else if (rc != SFGPU_OK) {
+                SF_FATAL("GPU %d: %s", g, sfgpu_strerror(core->gpu[g]));
+            }
+        }
+        if (bad) {
+            core->decode_fallbacks++;
+            db->heads_only = 0;
+            parse_db_mode(core, db, 0);
+            const int32_t keep = core->next_slot;
+            core->next_slot = db->slot; /* same slot again; the rotation of the batches in flight is not disturbed */
+            submit_db(core, db);
+            core->next_slot = keep;
+        }
+    }
     for (int g = 0; g < core->num_gpus; g++) {
         const int b = db->shard_begin[g];
         if (sfgpu_collect(core->gpu[g], db->slot, db->res + b) != SFGPU_OK) {
@@ -798,13 +874,15 @@ void free_db_tmp(db_t *db)
 void free_db(db_t *db)
 {
     for (int i = 0; i < db->capacity_rec; i++) {
-        free(db->mem_records[i]);
+        if (!db->mem_views)
+            free(db->mem_records[i]);
         free(db->rec[i].read_id);
         free(db->rec[i].raw_signal);
     }
     free(db->mem_records); free(db->mem_bytes); free(db->mem_cap); free(db->rec); free(db->res); free(db->aln);
     free(db->out); free(db->sig_off); free(db->sig_ptr); free(db->dig); free(db->off); free(db->rng);
     free(db->move_off); free(db->n_moves); free(db->win_start); free(db->win_len); free(db->moves);
+    free(db->sig_pos); free(db->sig_bytes); free(db->rec_bytes);
     free(db);
 }
 

@@ -18,6 +18,8 @@
 #include <errno.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include "s5read.h"
@@ -38,6 +40,9 @@ struct sf_s5file {
     char *line; /* ASCII line buffer */
     size_t line_cap;
     char errmsg[256];
+    /* binary files are mapped: records are handed out as views into the mapping (sf_s5_get_next_view) */
+    const uint8_t *map;
+    size_t map_len, map_pos;
 };
 
 static void set_err(sf_s5file_t *f, const char *msg) { snprintf(f->errmsg, sizeof f->errmsg, "%s", msg); }
@@ -150,6 +155,18 @@ sf_s5file_t *sf_s5_open(const char *path, char *err, size_t errcap)
         buf[hlen] = 0;
         parse_text_header(f, buf);
         free(buf);
+        /* map the file; when that is not possible (a pipe, ...) the stdio reader below is used */
+        struct stat st;
+        const long pos = ftell(fp);
+        if (pos > 0 && fstat(fileno(fp), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > pos) {
+            void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(fp), 0);
+            if (m != MAP_FAILED) {
+                f->map = (const uint8_t *)m;
+                f->map_len = (size_t)st.st_size;
+                f->map_pos = (size_t)pos;
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+            }
+        }
         return f;
     }
     /* ASCII: header lines start with '#' or '@' */
@@ -189,6 +206,8 @@ void sf_s5_close(sf_s5file_t *f)
 {
     if (!f)
         return;
+    if (f->map)
+        munmap((void *)f->map, f->map_len);
     if (f->fp)
         fclose(f->fp);
     for (int i = 0; i < f->n_attr; i++) {
@@ -231,8 +250,50 @@ static int reserve(char **mem, size_t *cap, size_t need)
     return 0;
 }
 
+int sf_s5_is_mapped(const sf_s5file_t *f) { return f->map != NULL; }
+
+/* next raw record of a mapped binary file as a view into the mapping (valid until sf_s5_close): no copy, the pages
+ * are touched by whoever reads the record.  Returns its size, 0 at end of file, < 0 on error. */
+int64_t sf_s5_get_next_view(sf_s5file_t *f, const char **ptr)
+{
+    if (!f->map)
+        return -1;
+    const size_t left = f->map_len - f->map_pos;
+    if (left < 8) {
+        if (left == 5 && !memcmp(f->map + f->map_pos, "5WOLB", 5))
+            return 0;
+        set_err(f, left == 0 ? "BLOW5 end-of-file marker missing (truncated file?)" : "truncated BLOW5 record header");
+        return -2;
+    }
+    uint64_t sz;
+    memcpy(&sz, f->map + f->map_pos, 8);
+    if (sz == 0 || sz > ((uint64_t)1 << 40)) {
+        set_err(f, "corrupt BLOW5 record size");
+        return -2;
+    }
+    if (sz > left - 8) {
+        set_err(f, "truncated BLOW5 record");
+        return -2;
+    }
+    *ptr = (const char *)(f->map + f->map_pos + 8);
+    f->map_pos += 8 + (size_t)sz;
+    return (int64_t)sz;
+}
+
 int64_t sf_s5_get_next_mem(sf_s5file_t *f, char **mem, size_t *cap)
 {
+    if (f->map) { /* keep the two readers on one cursor */
+        const char *p = NULL;
+        const int64_t n = sf_s5_get_next_view(f, &p);
+        if (n <= 0)
+            return n;
+        if (reserve(mem, cap, (size_t)n)) {
+            set_err(f, "out of memory");
+            return -2;
+        }
+        memcpy(*mem, p, (size_t)n);
+        return n;
+    }
     if (f->binary) {
         uint64_t sz = 0;
         unsigned char b[8];
@@ -434,6 +495,81 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
     }
     return 0;
 }
+
+/* Reads only the head of a binary record: read id, scaling, sample count, and where the signal field lies in the
+ * decompressed record (the device decodes the rest, sfgpu_submit_records).  A zlib record is inflated just far
+ * enough (its first SF_S5_HEAD_MAX output bytes). */
+#define SF_S5_HEAD_MAX 384 /* 2 + id (<= 255) + 4 + 32 + 8 + 4 bytes of the svb-zd stream, with room to spare */
+int sf_s5_parse_head(const sf_s5file_t *f, const char *mem, size_t bytes, sf_rec_t *r, int32_t *sig_pos, int64_t *sig_bytes,
+                     char **scratch, size_t *scratch_cap)
+{
+    if (!f->binary)
+        return -1;
+    const uint8_t *p = (const uint8_t *)mem;
+    size_t n = bytes;
+    int complete = 1; /* p[0 .. n) is the whole record */
+    if (f->record_press == 1) {
+        const size_t hdr = (sizeof(sf_inflater) + 63) & ~(size_t)63;
+        const int fresh = *scratch_cap == 0;
+        if (reserve(scratch, scratch_cap, hdr + SF_S5_HEAD_MAX + 16))
+            return -1;
+        if (fresh)
+            memset(*scratch, 0, hdr);
+        uint8_t *out = (uint8_t *)*scratch + hdr;
+        size_t got = 0;
+        const int rc = sf_zlib_inflate((sf_inflater *)*scratch, (const uint8_t *)mem, bytes, out, SF_S5_HEAD_MAX, &got);
+        if (rc < 0)
+            return -1; /* the caller falls back to the full decoder (which lets zlib have the last word) */
+        complete = rc == 0;
+        p = out;
+        n = got;
+    }
+    uint16_t idl;
+    if (n < 2)
+        return -1;
+    memcpy(&idl, p, 2);
+    size_t o = 2;
+    if ((size_t)idl + 4 + 32 + 8 > n - o)
+        return -1;
+    free(r->read_id);
+    r->read_id = (char *)malloc((size_t)idl + 1);
+    memcpy(r->read_id, p + o, idl);
+    r->read_id[idl] = 0;
+    o += idl;
+    o += 4; /* read_group */
+    memcpy(&r->digitisation, p + o, 8); o += 8;
+    memcpy(&r->offset, p + o, 8); o += 8;
+    memcpy(&r->range, p + o, 8); o += 8;
+    memcpy(&r->sampling_rate, p + o, 8); o += 8;
+    uint64_t len;
+    memcpy(&len, p + o, 8); o += 8;
+    *sig_pos = (int32_t)o;
+    if (f->signal_press == 0) {
+        if (len > SF_S5_MAX_SAMPLES || (complete && len > (n - o) / 2))
+            return -1;
+        r->len_raw_signal = len;
+        *sig_bytes = (int64_t)len * 2;
+    } else {
+        if (len > ((uint64_t)1 << 33) || (complete && len > n - o))
+            return -1;
+        uint32_t count = 0;
+        if (len >= 4) {
+            if (n - o < 4)
+                return -1;
+            memcpy(&count, p + o, 4);
+        } else if (len != 0) {
+            return -1;
+        }
+        if ((uint64_t)count > SF_S5_MAX_SAMPLES || 4 + ((uint64_t)count + 3) / 4 > (len ? len : 4))
+            return -1;
+        r->len_raw_signal = count;
+        *sig_bytes = (int64_t)len;
+    }
+    return 0;
+}
+
+uint8_t sf_s5_record_press(const sf_s5file_t *f) { return f->record_press; }
+uint8_t sf_s5_signal_press(const sf_s5file_t *f) { return f->signal_press; }
 
 static int parse_ascii(char *line, sf_rec_t *r)
 {

@@ -56,6 +56,7 @@ typedef struct {
     int64_t batch_size_bytes; /* -B */
     char *pore;
     int8_t pore_flag;
+    int8_t device_decode; /* --device-decode=yes|no (default yes): decode BLOW5 records on the GPUs */
     int32_t num_thread; /* -t: host threads decoding records */
     int8_t verbosity;
     int32_t debug_break;
@@ -106,10 +107,16 @@ typedef struct {
     char **mem_records;
     size_t *mem_bytes;
     size_t *mem_cap;
+    int mem_views;      /* mem_records[] point into the mapped file (not owned, read only) */
     sf_rec_t *rec;
     sfgpu_result_t *res; /* device results of the batch */
     aln_t *aln;
     char **out;
+    /* records decoded on the device: where the signal field lies in each decompressed record */
+    int32_t *sig_pos;
+    int64_t *sig_bytes;
+    int64_t *rec_bytes;
+    int heads_only;     /* parse_db read only the heads of this batch's records */
     /* packing scratch */
     int64_t *sig_off;   /* per-read sample counts */
     int16_t **sig_ptr;  /* per-read signal buffers */
@@ -149,6 +156,8 @@ typedef struct {
     sfgpu_ctx *gpu[SFHOST_MAX_GPUS];
     int32_t next_slot;
     double cells; /* DTW cells computed so far */
+    int device_decode;        /* BLOW5 records are inflated / svb-zd decoded on the GPUs (sfgpu_submit_records) */
+    int64_t decode_fallbacks; /* batches the host had to decode after all */
 } core_t;
 
 typedef struct {

@@ -9,7 +9,8 @@
  * (slow5lib src/slow5_press.c); the output here is byte-identical and the Adler-32 trailer is verified the same
  * way.  s5read.c falls back to zlib for any stream this decoder rejects.
  *
- * Return values of sf_zlib_inflate(): 0 = ok, 1 = output buffer too small, -1 = corrupt / unsupported stream. */
+ * Return values of sf_zlib_inflate(): 0 = ok, 1 = output buffer too small (the first *n_out bytes of the output are
+ * valid: this is how the head of a record is read without inflating the rest), -1 = corrupt / unsupported stream. */
 #include "sfinflate.h"
 
 #include <string.h>
@@ -251,7 +252,7 @@ int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out
             if ((len ^ nlen) != 0xffffu || (size_t)(in_end - ip) < len)
                 return -1;
             if ((size_t)(out_end - op) < len)
-                return 1;
+                { *n_out = (size_t)(op - out); return 1; }
             memcpy(op, ip, len);
             op += len;
             ip += len;
@@ -442,7 +443,7 @@ int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out
             }
             if (E_TYPE(e) == T_LITERAL) {
                 if (op >= out_end)
-                    return 1;
+                    { *n_out = (size_t)(op - out); return 1; }
                 *op++ = (uint8_t)E_VALUE(e);
                 /* >= 41 bits are left: a second and a third literal need no refill */
                 e = lt[BITS(LITLEN_BITS)];
@@ -481,7 +482,7 @@ int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out
             if (dist > (size_t)(op - out))
                 return -1;
             if (len > (size_t)(out_end - op))
-                return 1;
+                { *n_out = (size_t)(op - out); return 1; }
             const uint8_t *src = op - dist;
             if (dist >= 8 && (size_t)(out_end - op) >= len + 8) {
                 /* whole words; may write up to 7 bytes past the match, inside the buffer */

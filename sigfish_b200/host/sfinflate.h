@@ -26,7 +26,8 @@ typedef struct {
 } sf_inflater;
 
 /* Inflates the zlib stream in[0 .. n_in) into out[0 .. cap_out); *n_out = bytes produced.
- * 0 = ok (Adler-32 verified), 1 = cap_out too small, -1 = corrupt or unsupported stream. */
+ * 0 = ok (Adler-32 verified), 1 = cap_out too small (out[0 .. *n_out) is the valid beginning of the output),
+ * -1 = corrupt or unsupported stream. */
 int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap_out, size_t *n_out);
 
 #ifdef __cplusplus

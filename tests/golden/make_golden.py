@@ -175,6 +175,9 @@ def main():
     for name, src in (("sp1_dna", "sp1_dna.blow5"), ("sequin_rna", "sequin_rna.blow5")):
         ids, sigs, sc = read_blow5(os.path.join(REFDIR, src))
         save_reads(os.path.join(HERE, name + ".npz"), ids, sigs, sc)
+    # the small DNA file itself (22 KB: zlib records, svb-zd signals, auxiliary fields, written by slow5lib): input of
+    # the device-side record decoder tests
+    shutil.copyfile(os.path.join(REFDIR, "sp1_dna.blow5"), os.path.join(HERE, "sp1_dna.blow5"))
     for name, src in (("nCoV-2019", "nCoV-2019.reference.fasta"), ("rnasequin", "rnasequin_sequences_2.4.fa")):
         with open(os.path.join(REFDIR, src), "rb") as fi, gzip.GzipFile(os.path.join(HERE, name + ".fa.gz"), "wb", mtime=0) as fo:
             shutil.copyfileobj(fi, fo)

@@ -383,3 +383,51 @@ def test_header_read_group_count_cannot_grow_after_attributes(host, tmp_path):
     # an absurd count in the binary header is refused at open
     _blow5_with_record(p, body, False, False, num_groups=0x7fffffff)
     assert not host.sf_s5_open(p.encode(), err, 512)
+
+
+@pytest.mark.parametrize("fmt", ["blow5_zlib_svb", "blow5_zlib_raw", "blow5_none_svb", "blow5_none_raw", "reference_file"])
+def test_record_heads_agree_with_full_decode(host, tmp_path, fmt):
+    """sf_s5_parse_head (what the host reads when the GPUs decode the records): id, scaling and sample count equal
+    the full decoder's, and the signal field it points at really is the signal (checked by decoding it here)"""
+    import struct
+    import zlib
+    host.sf_s5_parse_head.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(SfRec), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    host.sf_s5_get_next_view.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    host.sf_s5_get_next_view.restype = C.c_int64
+    host.sf_s5_is_mapped.argtypes = [C.c_void_p]
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, "sp1_dna.npz"))
+    if fmt == "reference_file":
+        p = os.path.join(H.GOLDEN, "sp1_dna.blow5")
+        zl, svb = True, True
+    else:
+        sigs = list(sigs) + [np.zeros(0, np.int16), np.array([-32768, 32767, 0, -1, 1], np.int16)]
+        ids = ids + ["empty", "extremes"]
+        sc = sc + [sc[0], sc[0]]
+        p = str(tmp_path / "r.blow5")
+        zl, svb = "zlib" in fmt, "svb" in fmt
+        synth.write_blow5(p, ids, sigs, scalings=sc, record_zlib=zl, signal_svb=svb)
+    err = C.create_string_buffer(512)
+    f = host.sf_s5_open(p.encode(), err, 512)
+    assert f and host.sf_s5_is_mapped(f) == 1
+    scratch, scap = C.c_void_p(), C.c_size_t(0)
+    for i in range(len(ids)):
+        view = C.c_void_p()
+        n = host.sf_s5_get_next_view(f, C.byref(view))
+        assert n > 0
+        rec, pos, nbytes = SfRec(), C.c_int32(), C.c_int64()
+        assert host.sf_s5_parse_head(f, view, n, C.byref(rec), C.byref(pos), C.byref(nbytes), C.byref(scratch), C.byref(scap)) == 0
+        assert rec.read_id.decode() == ids[i]
+        assert (rec.digitisation, rec.offset, rec.range) == (sc[i]["digitisation"], sc[i]["offset"], sc[i]["range"])
+        assert rec.len_raw_signal == len(sigs[i])
+        raw = C.string_at(view, n)
+        body = zlib.decompress(raw) if zl else raw
+        field = body[pos.value:pos.value + nbytes.value]
+        assert len(field) == nbytes.value
+        if svb:
+            assert struct.unpack("<I", field[:4])[0] == len(sigs[i])
+            assert field == synth._svb_zd_encode(np.asarray(sigs[i], np.int16))
+        else:
+            assert field == np.asarray(sigs[i], np.int16).tobytes()
+    assert host.sf_s5_get_next_view(f, C.byref(view)) == 0
+    host.sf_s5_close(f)

@@ -50,6 +50,35 @@ int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_
     return SFGPU_OK;
 }
 
+/* records decoded on the device: the host's part is the copy of the compressed bytes into the staging buffer */
+int sfgpu_submit_records(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const uint8_t *const *records, const int64_t *record_bytes,
+                         int32_t record_press, int32_t signal_press, const int32_t *sig_pos, const int64_t *sig_bytes,
+                         const int64_t *n_samples, const float *digitisation, const float *offset, const float *range)
+{
+    (void)record_press; (void)signal_press; (void)sig_pos; (void)sig_bytes; (void)n_samples;
+    (void)digitisation; (void)offset; (void)range;
+    if (slot < 0 || slot >= NULL_SLOTS)
+        return SFGPU_EARG;
+    int64_t tot = 0;
+    for (int32_t i = 0; i < n_reads; i++)
+        tot += (record_bytes[i] + 7) & ~7ll;
+    tot = (tot + 1) / 2; /* the staging buffer is counted in int16 */
+    if (tot > c->cap[slot]) {
+        free(c->stage[slot]);
+        c->cap[slot] = tot + tot / 4;
+        c->stage[slot] = malloc(sizeof(int16_t) * c->cap[slot]);
+        if (!c->stage[slot])
+            return SFGPU_ELIMIT;
+    }
+    int64_t o = 0;
+    for (int32_t i = 0; i < n_reads; i++) {
+        memcpy((char *)c->stage[slot] + o, records[i], (size_t)record_bytes[i]);
+        o += (record_bytes[i] + 7) & ~7ll;
+    }
+    c->n[slot] = n_reads;
+    return SFGPU_OK;
+}
+
 int sfgpu_submit_reads(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const int16_t *const *signals,
                        const int64_t *n_samples, const float *digitisation, const float *offset, const float *range)
 {
