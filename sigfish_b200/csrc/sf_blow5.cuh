@@ -209,6 +209,8 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
             const uint32_t nlen = sf_bits_take(b, 16);
             if ((len ^ nlen) != 0xffffu)
                 return SF_REC_EBLOCK;
+            if ((int64_t)len > 4 * (b.n_words + 2 - b.w) + 8)
+                return SF_REC_EBLOCK; // more bytes than the record has left
             for (uint32_t k = 0; k < len; k++) {
                 sf_bits_refill(b);
                 const uint32_t v = sf_bits_take(b, 8);
@@ -249,6 +251,8 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
             int n = 0, prev = 0;
             while (n < n_lit + n_dist) {
                 sf_bits_refill(b);
+                if (b.w > b.n_words + 2)
+                    return SF_REC_ECODE;
                 const int sym = sf_decode_sym(b, pt, 7, longl, 0);
                 if (sym < 0)
                     return SF_REC_ECODE;
@@ -288,6 +292,9 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
 
         for (;;) {
             sf_bits_refill(b);
+            // a damaged stream can decode the zero padding past its end for ever: stop two words beyond the record
+            if (b.w > b.n_words + 2)
+                return SF_REC_ESYMBOL;
             int sym = sf_decode_sym(b, lt, SF_INF_LBITS, longl, nl_long);
             if (sym < 0)
                 return SF_REC_ESYMBOL;
