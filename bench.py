@@ -68,7 +68,7 @@ ROWS_PER_LANE = 16
 FLOOR_SLOTS_PER_CELL = 4.0
 # DRAM traffic of one DTW launch from the committed `ncu --set full` capture (dram__bytes_read.sum +
 # dram__bytes_write.sum at 8288 reads); almost all of it is wavefront checkpoints.  NOT measured in this run.
-NCU_DTW_TRAFFIC = {"reads": 8288, "bytes": 144.03328e6 + 4778.365e6, "source": "profiles/r01_ncu_summary.md"}
+NCU_DTW_TRAFFIC = {"reads": 8288, "bytes": 357.556992e6 + 5078.331e6, "source": "profiles/r02_ncu_summary.md"}
 
 
 def make_inputs(shape: str, n_unique: int, seed: int, ref_len: int = REF_LEN):
@@ -486,7 +486,7 @@ def main():
                          "traffic_measured_in_this_run": False,
                          "traffic_source": NCU_DTW_TRAFFIC["source"] + " (ncu --set full at 8288 reads, scaled by reads); "
                                            "algorithmic HBM bytes are 0.016 B/cell (8 MB reference stream, L2 resident) "
-                                           "plus the wavefront checkpoints (0.59 MB/read)",
+                                           "plus the wavefront checkpoints and the pieces' warm fronts (0.66 MB/read)",
                          "frac_of_own_instruction_stream": dtw_cells_per_s / own_peak,
                          "own_instruction_stream": f"{ISSUE_SLOTS_PER_STEP:.0f} issue slots per 32x{ROWS_PER_LANE} cells "
                                                    f"({SASS_PER_STEP:.0f} SASS per column, the {ROWS_PER_LANE} half-rate FMNMX3 counted twice)",

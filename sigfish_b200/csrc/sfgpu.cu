@@ -224,12 +224,27 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         s.cap_samples = cap;
     }
     if (n_reads > s.cap_reads) {
-        const int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
+        int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
         dfree(s.d_off); dfree(s.d_scal); dfree(s.d_ev_start); dfree(s.d_ev_mean); dfree(s.d_ev_len);
         dfree(s.d_queries); dfree(s.d_info); dfree(s.d_ckpt); dfree(s.d_hits); dfree(s.d_polya); dfree(s.d_win_start); dfree(s.d_win_len);
         dfree(s.d_list_full); dfree(s.d_list_other);
         s.cap_reads = 0;
+        {
+            // the per-read device buffers of a slot (the wavefront checkpoints are the bulk: ~0.66 MB per read on
+            // a long reference): refuse a batch that cannot fit instead of dying inside cudaMalloc, and give up the
+            // 25 % growth margin when only the batch itself fits
+            const double per_read = (double)c->ev_cap * 16.0 + (double)c->q_cap * 4.0 * ((c->opt.flags & SFGPU_SAM) ? 4.0 : 1.0) +
+                                    (double)c->ck_per_read * c->ck_floats * 4.0 + 256.0;
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                if (per_read * (double)n_reads > 0.95 * (double)free_b)
+                    return fail(c, SFGPU_ELIMIT, "a batch of %d reads needs %.1f GB of device memory per slot, %.1f GB are free: "
+                                "use a smaller batch (-K)", n_reads, per_read * n_reads / 1e9, free_b / 1e9);
+                if (per_read * (double)cap > 0.95 * (double)free_b)
+                    cap = std::max<int32_t>(n_reads, 64);
+            }
+        }
         const size_t n = (size_t)cap;
         SF_CUDA(c, cudaMallocHost(&s.h_off, sizeof(int64_t) * (2 * n + 1)));
         SF_CUDA(c, cudaMallocHost(&s.h_scal, sizeof(float) * 3 * n));
@@ -1644,8 +1659,13 @@ int sfgpu_collect_paths(sfgpu_ctx *c, int32_t slot, const int64_t *move_off, uin
         pa.n_moves = d_n;
         pa.start_col = d_sc;
         cudaError_t e = cudaErrorInvalidValue;
+        g_trace(c->opt.device, "collect_paths: buffers ready");
         SF_DISPATCH_R(c->R, std_dtw, (e = launch_path<R, STD>(pa, s.stream)));
         SF_CUDA(c, e);
+        if (g_trace.on) {
+            SF_CUDA(c, cudaStreamSynchronize(s.stream));
+            g_trace(c->opt.device, "collect_paths: path kernel done");
+        }
         if (total_moves > 0)
             SF_CUDA(c, cudaMemcpyAsync(moves, d_moves, (size_t)total_moves, cudaMemcpyDeviceToHost, s.stream));
         SF_CUDA(c, cudaMemcpyAsync(n_moves, d_n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
@@ -1653,6 +1673,7 @@ int sfgpu_collect_paths(sfgpu_ctx *c, int32_t slot, const int64_t *move_off, uin
         SF_CUDA(c, cudaMemcpyAsync(ws.data(), s.d_win_start, sizeof(uint64_t) * ws.size(), cudaMemcpyDeviceToHost, s.stream));
         SF_CUDA(c, cudaMemcpyAsync(wl.data(), s.d_win_len, sizeof(float) * wl.size(), cudaMemcpyDeviceToHost, s.stream));
         SF_CUDA(c, cudaStreamSynchronize(s.stream));
+        g_trace(c->opt.device, "collect_paths: copied back");
         return SFGPU_OK;
     }();
     dfree(d_dirs); dfree(d_dir_off); dfree(d_move_off); dfree(d_moves); dfree(d_n); dfree(d_sc);

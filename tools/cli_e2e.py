@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--ref-len", type=int, default=1_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("-K", type=int, default=0)
+    ap.add_argument("--auto-batch", action="store_true", help="leave -K / -B to the command line's own choice")
     ap.add_argument("--trace", default="", help="write the CLI's stderr (--verbose 5, SFGPU_TRACE=1) to this file")
     args = ap.parse_args()
     B.build_all()
@@ -33,17 +34,31 @@ def main():
     k = 9
     mean, stdv = synth.make_model(k)
     seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
-    sigs, _ = synth.simulate_reads([seq], k, mean, args.reads, seed=4242, bases_per_read=450)
+    # a unit of at most 8288 distinct reads, its records repeated up to --reads (writing BLOW5 from Python costs
+    # 0.5 ms per read, which on a multi-GPU box is paid per GPU-minute)
+    unit = min(args.reads, 8288)
+    sigs, _ = synth.simulate_reads([seq], k, mean, unit, seed=4242, bases_per_read=450)
     ids = [f"read_{i:06d}" for i in range(len(sigs))]
     synth.write_model_file(os.path.join(d, "model.txt"), k, mean, stdv)
     synth.write_fasta(os.path.join(d, "ref.fa"), ["chrS"], [seq])
-    synth.write_blow5(os.path.join(d, "reads.blow5"), ids, sigs, kit="sqk-lsk114")
+    one = os.path.join(d, "unit.blow5")
+    synth.write_blow5(one, ids, sigs, kit="sqk-lsk114")
+    raw = open(one, "rb").read()
+    hlen = 64 + 4 + int.from_bytes(raw[64:68], "little")
+    reps = max(1, round(args.reads / unit))
+    args.reads = reps * unit
+    with open(os.path.join(d, "reads.blow5"), "wb") as f:
+        f.write(raw[:hlen])
+        for _ in range(reps):
+            f.write(raw[hlen:-5])
+        f.write(b"5WOLB")
     K = args.K or args.reads
     out = {"reads": args.reads, "gpus": args.gpus, "cells_per_read": 250 * 2 * (args.ref_len + 1 - k)}
 
     t0 = time.perf_counter()
     r = subprocess.run([B.CLI, "dtw", os.path.join(d, "ref.fa"), os.path.join(d, "reads.blow5"), "--kmer-model",
-                        os.path.join(d, "model.txt"), "-K", str(K), "-B", "100G", "-t", str(os.cpu_count() or 8), "--gpus", str(args.gpus),
+                        os.path.join(d, "model.txt")] + ([] if args.auto_batch else ["-K", str(K), "-B", "100G"]) +
+                       ["-t", str(os.cpu_count() or 8), "--gpus", str(args.gpus),
                         "-o", os.path.join(d, "gpu.paf")] + (["--verbose", "5"] if args.trace else []),
                        capture_output=True, text=True, env=dict(os.environ, **({"SFGPU_TRACE": "1"} if args.trace else {})))
     if args.trace:

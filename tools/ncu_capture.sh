@@ -14,7 +14,7 @@ timeout 120 $CLI $ARGS > /dev/null 2>&1 || exit 1
 # 1. every launch of the command line with its device time
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_cli_c4.csv $CLI $ARGS > /dev/null 2>&1
 # 2. full reports of the kernels of that run
-timeout 900 ncu --set full --clock-control none --import-source on \
+timeout 900 ncu --set full --clock-control none \
     -k regex:'sf_dtw_pair_kernel|sf_inflate_kernel|sf_signal_kernel|sf_events_kernel|sf_trace_pair_kernel|sf_verify_kernel|sf_ref_stats_kernel' \
     -o $out/${tag}_prof_cli_c4 -f $CLI $ARGS > /dev/null 2>&1
 # 3. --sam: the path kernel
@@ -24,4 +24,10 @@ timeout 600 ncu --set full --clock-control none -k regex:sf_path_kernel -c 1 -o 
 timeout 300 python tools/perf_sweep.py c2 c5 --reads 4096 > $out/${tag}_ncu_sweep_plain.txt 2>&1 && \
 timeout 900 ncu --set full --clock-control none -k regex:'sf_dtw_pair_kernel|sf_dtw_score_kernel|sf_events_kernel|sf_trace' -c 14 \
     -o $out/${tag}_prof_c2_c5 -f python tools/perf_sweep.py c2 c5 --reads 4096 > /dev/null 2>&1
+# the reports are large (tens of MB each; gpurun brings back 64 MiB at most): keep the metric tables, drop the reports
+python tools/ncu_summary.py $out/${tag}_prof_cli_c4.ncu-rep $out/${tag}_prof_path.ncu-rep $out/${tag}_prof_c2_c5.ncu-rep > $out/${tag}_ncu_summary.md 2> $out/${tag}_ncu_summary_err.txt
+for r in prof_cli_c4 prof_path prof_c2_c5; do
+    ncu -i $out/${tag}_$r.ncu-rep --page raw --csv > $out/${tag}_$r.raw.csv 2>/dev/null
+done
+rm -f $out/*.ncu-rep
 ls -la $out | grep ${tag}_
