@@ -209,9 +209,11 @@ void slot_free_buffers(sf_slot &s)
     s.cap_res = s.cap_warm = s.cap_bad = 0;
 }
 
-int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
+// host_signal: the batch arrives as int16 samples (a pinned staging buffer is needed); false when the device
+// decodes the records itself -- pinning ~100 MB that nobody writes costs tens of ms per slot
+int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples, bool host_signal = true)
 {
-    const bool grow = n_samples > s.cap_samples || n_reads > s.cap_reads;
+    const bool grow = n_samples > s.cap_samples || n_reads > s.cap_reads || (host_signal && !s.h_signal);
     if (grow)
         g_trace(c->opt.device, "slot_reserve: growing buffers");
     if (n_samples > s.cap_samples) {
@@ -219,10 +221,11 @@ int slot_reserve(sfgpu_ctx *c, sf_slot &s, int32_t n_reads, int64_t n_samples)
         hfree(s.h_signal);
         dfree(s.d_signal);
         s.cap_samples = 0;
-        SF_CUDA(c, cudaMallocHost(&s.h_signal, sizeof(int16_t) * cap));
         SF_CUDA(c, cudaMalloc(&s.d_signal, sizeof(int16_t) * cap));
         s.cap_samples = cap;
     }
+    if (host_signal && !s.h_signal)
+        SF_CUDA(c, cudaMallocHost(&s.h_signal, sizeof(int16_t) * s.cap_samples));
     if (n_reads > s.cap_reads) {
         int32_t cap = std::max<int32_t>(n_reads + n_reads / 4, 64);
         hfree(s.h_off); hfree(s.h_scal); hfree(s.h_info); hfree(s.h_hits); hfree(s.h_queries);
@@ -1393,7 +1396,7 @@ int sfgpu_submit_records(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const uint
         padded += (ns + 7) & ~7ll;
         raw += ns;
     }
-    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8);
+    rc = slot_reserve(c, s, std::max(n_reads, 1), padded + 8, false);
     if (rc)
         return rc;
     if ((size_t)rec_total + 16 > s.cap_rec) {

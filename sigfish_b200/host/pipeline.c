@@ -380,6 +380,9 @@ ret_status_t load_db(core_t *core, db_t *db)
         db->total_reads++;
         db->sum_bytes += got;
     }
+    if (db->mem_views && db->n_rec > 0) /* records of a batch are contiguous in the file */
+        sf_s5_prefault(core->sf, db->mem_records[0],
+                       (size_t)(db->mem_records[db->n_rec - 1] - db->mem_records[0]) + db->mem_bytes[db->n_rec - 1]);
     status.num_reads = db->n_rec;
     status.num_bytes = db->sum_bytes;
     core->load_db_time += sf_realtime() - t0;

@@ -252,6 +252,22 @@ static int reserve(char **mem, size_t *cap, size_t need)
 
 int sf_s5_is_mapped(const sf_s5file_t *f) { return f->map != NULL; }
 
+/* maps the pages of [ptr, ptr + len) of the mapped file into this process now (from the loader thread), so that the
+ * threads that copy the records to the GPUs' staging buffers do not take the page faults; best effort */
+void sf_s5_prefault(const sf_s5file_t *f, const char *ptr, size_t len)
+{
+#ifdef MADV_POPULATE_READ
+    if (!f->map || !len)
+        return;
+    const uintptr_t page = 4096, a = (uintptr_t)ptr & ~(page - 1), e = ((uintptr_t)ptr + len + page - 1) & ~(page - 1);
+    const uintptr_t lo = (uintptr_t)f->map, hi = ((uintptr_t)f->map + f->map_len + page - 1) & ~(page - 1);
+    if (a >= lo && e <= hi)
+        (void)madvise((void *)a, (size_t)(e - a), MADV_POPULATE_READ);
+#else
+    (void)f; (void)ptr; (void)len;
+#endif
+}
+
 /* next raw record of a mapped binary file as a view into the mapping (valid until sf_s5_close): no copy, the pages
  * are touched by whoever reads the record.  Returns its size, 0 at end of file, < 0 on error. */
 int64_t sf_s5_get_next_view(sf_s5file_t *f, const char **ptr)

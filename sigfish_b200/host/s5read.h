@@ -27,6 +27,7 @@ int64_t sf_s5_get_next_mem(sf_s5file_t *f, char **mem, size_t *cap);
  * copies (same cursor as sf_s5_get_next_mem) */
 int sf_s5_is_mapped(const sf_s5file_t *f);
 int64_t sf_s5_get_next_view(sf_s5file_t *f, const char **ptr);
+void sf_s5_prefault(const sf_s5file_t *f, const char *ptr, size_t len);
 /* decodes a raw record (slow5_rec_depress_parse).  Thread safe for distinct rec/scratch; modifies
  * mem for ASCII records. */
 int sf_s5_parse(const sf_s5file_t *f, char *mem, size_t bytes, sf_rec_t *rec, char **scratch, size_t *scratch_cap);
