@@ -336,17 +336,20 @@ int dtw_main(int argc, char *argv[])
 
     core_t *core = init_core(fastafile, slow5file, opt, realtime0);
     /* Batch size: -K / -B are honoured when given (long references are cut into pieces, so any batch fills the
-     * GPU).  Otherwise a batch is about 1e12 DTW cells per GPU (~0.12 s of device time, so that the
-     * fixed costs of a batch -- launches, the tail of the last tasks, the host epilogue -- stay small), at least
-     * two full waves of DTW tasks and at most 65536 reads per GPU. */
+     * GPU).  Otherwise a batch is about 1e12 DTW cells per GPU (~0.12 s of device time: long enough
+     * for the fixed costs of a batch -- launches, the tail of the last tasks, the host epilogue -- to stay small,
+     * short enough for the GPUs to start early: on 8 GPUs a first batch of two waves per GPU kept them idle for
+     * 0.33 s while it was read, allocated for and staged), at least half a wave and at most 65536 reads per GPU. */
     if (!k_set) {
         const int32_t wave = sfgpu_wave_reads(core->gpu[0]);
         const double cells_per_read = (double)core->opt.query_size * (double)sfgpu_ref_columns(core->gpu[0]);
         int64_t per_gpu = cells_per_read > 0 ? (int64_t)(1e12 / cells_per_read) : 0;
         if (per_gpu > 65536)
             per_gpu = 65536;
-        if (per_gpu < 2ll * wave)
-            per_gpu = 2ll * wave;
+        if (per_gpu < wave / 2)
+            per_gpu = wave / 2;
+        if (per_gpu < 64)
+            per_gpu = 64;
         const int64_t want = per_gpu * core->num_gpus;
         if (want > core->opt.batch_size)
             core->opt.batch_size = (int32_t)(want > 262144 ? 262144 : want);
