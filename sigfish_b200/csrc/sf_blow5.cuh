@@ -14,15 +14,26 @@
 // of a block (canonical codes assigned with ballots, table entries written by the lane that owns the symbol) and
 // copying matches (byte k of a match comes from out[pos - dist + k % dist], which is already final for every k).
 // Tables live in shared memory: an 11-bit first-level table for the literal/length code and a 9-bit one for the
-// distance code; the few codes longer than that (rare symbols by construction) are kept in a short list that is
-// searched linearly.  Literals are stored by lane 0.
+// distance code; the codes longer than that are kept in a short list that is searched linearly.  Literals are stored
+// by lane 0.  The grid is exactly the resident blocks (7 per SM): with one more block per SM that block ran alone
+// after the others had finished (-24 % together with the funnel-shift bit reader).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
 
 #define SF_INF_WARPS 4
+// first-level table bits.  Measured on 65 536 records of 4.5 k samples (tools/decode_bench.py, one call, same box):
+// 10 / 8 bits 39.3 ms, 11 / 9 bits 23.4 ms, 12 / 9 bits 25.1 ms (fewer resident warps): codes of 11 bits are common
+// enough in these streams that sending them through the long-code list costs more than the larger table
+#ifndef SF_INF_LBITS
 #define SF_INF_LBITS 11
+#endif
+#ifndef SF_INF_DBITS
 #define SF_INF_DBITS 9
+#endif
+#ifndef SF_INF_MINB
+#define SF_INF_MINB 1
+#endif
 #define SF_INF_LONG_L 288
 #define SF_INF_LONG_D 32
 // per-warp shared memory, in bytes: litlen table, dist table, precode table (u16 each), long-code lists (u32),
@@ -62,31 +73,50 @@ __constant__ uint16_t sf_k_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33,
 __constant__ uint8_t sf_k_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t sf_k_precode_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// the bit reader: 64-bit buffer fed with aligned 32-bit words; every lane holds the same state
+// The bit reader: a 64-bit window (lo, hi) over two consecutive aligned 32-bit words of the record and a bit position
+// bp < 32 inside it; every lane holds the same state.  peek = one funnel shift (32 valid bits at any time), take =
+// add to bp and slide the window when it crosses a word: no 64-bit shifts (two instructions each on the GPU) and no
+// separate refill step -- the decode loop of a literal is ~20 instructions instead of ~45 with a 64-bit bit buffer,
+// and the inflate kernel is instruction-issue bound (ncu: issue active 70 %).
 struct sf_bits {
     const uint32_t *in;  // record start (8-byte aligned)
-    int64_t n_words;     // words that hold record bytes
-    int64_t w;           // next word to load
-    uint64_t bb;
-    int bc;
+    int64_t n_words;     // words that hold record bytes; words past them read as zero (never consumed by a
+                         // well-formed stream: checked at the end)
+    int64_t w;           // next word to load (hi = word w - 1, lo = word w - 2)
+    uint32_t lo, hi;
+    int bp;
 };
-__device__ __forceinline__ void sf_bits_refill(sf_bits &b)
+__device__ __forceinline__ uint32_t sf_bits_word(const sf_bits &b, int64_t w) { return w < b.n_words ? __ldg(b.in + w) : 0u; }
+__device__ __forceinline__ void sf_bits_init(sf_bits &b, const uint8_t *rec, int64_t n_in, int skip_bits)
 {
-    if (b.bc <= 32) {
-        // words past the record read as zero: a well-formed stream never consumes them (checked at the end)
-        const uint32_t v = b.w < b.n_words ? __ldg(b.in + b.w) : 0u;
+    b.in = reinterpret_cast<const uint32_t *>(rec);
+    b.n_words = (n_in + 3) >> 2;
+    b.lo = sf_bits_word(b, 0);
+    b.hi = sf_bits_word(b, 1);
+    b.w = 2;
+    b.bp = skip_bits;
+}
+__device__ __forceinline__ uint32_t sf_bits_peek(const sf_bits &b) { return __funnelshift_r(b.lo, b.hi, b.bp); }
+__device__ __forceinline__ void sf_bits_drop(sf_bits &b, int n) // n <= 32
+{
+    b.bp += n;
+    if (b.bp >= 32) {
+        b.lo = b.hi;
+        b.hi = sf_bits_word(b, b.w);
         b.w++;
-        b.bb |= (uint64_t)v << b.bc;
-        b.bc += 32;
+        b.bp -= 32;
     }
 }
-__device__ __forceinline__ uint32_t sf_bits_take(sf_bits &b, int n)
+__device__ __forceinline__ uint32_t sf_bits_take(sf_bits &b, int n) // n <= 16
 {
-    const uint32_t v = (uint32_t)b.bb & ((1u << n) - 1u);
-    b.bb >>= n;
-    b.bc -= n;
+    const uint32_t v = sf_bits_peek(b) & ((1u << n) - 1u);
+    sf_bits_drop(b, n);
     return v;
 }
+__device__ __forceinline__ void sf_bits_refill(sf_bits &) {} // the window always holds >= 32 bits
+__device__ __forceinline__ int64_t sf_bits_used(const sf_bits &b) { return 32 * (b.w - 2) + b.bp; }
+// has the reader run well past the end of the record?  (a damaged stream can decode the zero padding for ever)
+__device__ __forceinline__ bool sf_bits_overrun(const sf_bits &b) { return b.w > b.n_words + 4; }
 
 // Canonical Huffman code -> first-level table (entry = symbol << 4 | length, 0 = none) plus a list of the codes
 // longer than `pbits` (entry = reversed code | length << 16 | symbol << 20).  lens[] in shared memory; every lane
@@ -149,19 +179,17 @@ __device__ __forceinline__ bool sf_build_table(const uint8_t *lens, const int n_
 // next symbol of a code; needs >= 15 bits in the buffer.  Returns -1 when no code matches.
 __device__ __forceinline__ int sf_decode_sym(sf_bits &b, const uint16_t *table, const int pbits, const uint32_t *longs, const int n_long)
 {
-    const uint32_t peek = (uint32_t)b.bb;
+    const uint32_t peek = sf_bits_peek(b);
     const uint16_t e = table[peek & ((1u << pbits) - 1u)];
     if (e) {
-        b.bb >>= (e & 15);
-        b.bc -= (e & 15);
+        sf_bits_drop(b, e & 15);
         return e >> 4;
     }
     for (int k = 0; k < n_long; k++) {
         const uint32_t L = longs[k];
         const int l = (L >> 16) & 15;
         if ((peek & ((1u << l) - 1u)) == (L & 0xffffu)) {
-            b.bb >>= l;
-            b.bc -= l;
+            sf_bits_drop(b, l);
             return (int)(L >> 20);
         }
     }
@@ -188,11 +216,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
     if ((cmf & 15) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20))
         return SF_REC_EHEADER;
     sf_bits b;
-    b.in = reinterpret_cast<const uint32_t *>(rec);
-    b.n_words = (n_in + 3) >> 2;
-    b.w = 1;
-    b.bb = (uint64_t)(__ldg(b.in) >> 16); // the two header bytes are done
-    b.bc = 16;
+    sf_bits_init(b, rec, n_in, 16); // the two header bytes are done
     int64_t op = 0;
     int last;
     do {
@@ -202,14 +226,12 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
         if (btype == 3)
             return SF_REC_EBLOCK;
         if (btype == 0) { // stored: to the byte boundary, LEN, ~LEN, bytes
-            sf_bits_take(b, b.bc & 7);
-            sf_bits_refill(b);
+            sf_bits_drop(b, (8 - (b.bp & 7)) & 7);
             const uint32_t len = sf_bits_take(b, 16);
-            sf_bits_refill(b);
             const uint32_t nlen = sf_bits_take(b, 16);
             if ((len ^ nlen) != 0xffffu)
                 return SF_REC_EBLOCK;
-            if ((int64_t)len > 4 * (b.n_words + 2 - b.w) + 8)
+            if ((int64_t)len > 4 * (b.n_words + 2 - b.w) + 16)
                 return SF_REC_EBLOCK; // more bytes than the record has left
             for (uint32_t k = 0; k < len; k++) {
                 sf_bits_refill(b);
@@ -251,7 +273,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
             int n = 0, prev = 0;
             while (n < n_lit + n_dist) {
                 sf_bits_refill(b);
-                if (b.w > b.n_words + 2)
+                if (sf_bits_overrun(b))
                     return SF_REC_ECODE;
                 const int sym = sf_decode_sym(b, pt, 7, longl, 0);
                 if (sym < 0)
@@ -292,8 +314,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
 
         for (;;) {
             sf_bits_refill(b);
-            // a damaged stream can decode the zero padding past its end for ever: stop two words beyond the record
-            if (b.w > b.n_words + 2)
+            if (sf_bits_overrun(b))
                 return SF_REC_ESYMBOL;
             int sym = sf_decode_sym(b, lt, SF_INF_LBITS, longl, nl_long);
             if (sym < 0)
@@ -326,7 +347,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
         }
     } while (!last);
     // every bit consumed must have come from the record
-    const int64_t used_bits = 32 * b.w - b.bc;
+    const int64_t used_bits = sf_bits_used(b);
     if (used_bits > 8 * n_in)
         return SF_REC_ESYMBOL;
     n_out = op;
@@ -358,7 +379,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
     return SF_REC_OK;
 }
 
-__global__ void __launch_bounds__(32 * SF_INF_WARPS) sf_inflate_kernel(const sf_rec_args a)
+__global__ void __launch_bounds__(32 * SF_INF_WARPS, SF_INF_MINB) sf_inflate_kernel(const sf_rec_args a)
 {
     extern __shared__ __align__(16) uint8_t sf_inf_smem[];
     const int lane = threadIdx.x & 31;

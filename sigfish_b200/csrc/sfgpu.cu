@@ -147,6 +147,7 @@ struct sfgpu_ctx {
     int32_t force_level_len = 0;  // test knob (reserved[4]): > 0 piece length in checkpoint periods, < 0 never split
     std::vector<sf_slot> slots;
     int dtw_blocks_per_sm = 0;
+    int inflate_blocks_per_sm = 8;
     char err[512];
 };
 
@@ -441,7 +442,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ra.status = s.d_status;
         SF_CUDA(c, cudaMemsetAsync(s.d_status, 0, sizeof(int32_t) * (size_t)n, st));
         if (s.record_press) {
-            const int blocks = std::max(1, std::min((n + SF_INF_WARPS - 1) / SF_INF_WARPS, c->sm_count * 8));
+            const int blocks = std::max(1, std::min((n + SF_INF_WARPS - 1) / SF_INF_WARPS, c->sm_count * c->inflate_blocks_per_sm));
             sf_inflate_kernel<<<blocks, 32 * SF_INF_WARPS, SF_INF_WARPS * SF_INF_SMEM_WARP, st>>>(ra);
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
@@ -1137,6 +1138,12 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         if (nb <= 0)
             return fail(c, SFGPU_ECUDA, "DTW kernel does not fit on the device (R=%d)", rows);
         c->dtw_blocks_per_sm = nb;
+        {
+            int ib = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ib, sf_inflate_kernel, 32 * SF_INF_WARPS,
+                                                              SF_INF_WARPS * SF_INF_SMEM_WARP) == cudaSuccess && ib > 0)
+                c->inflate_blocks_per_sm = ib;
+        }
         c->ck_floats = sf_ckpt_floats(rows);
         // Two full-length reads per warp (16 lanes x 16 rows each) where that beats one read per warp: the pair layout
         // computes 256 rows per read whatever q is, so its useful rate falls as q/256 (measured on the 1 Mb shape:

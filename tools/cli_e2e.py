@@ -25,13 +25,16 @@ def main():
     ap.add_argument("--ref-len", type=int, default=1_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("-K", type=int, default=0)
+    ap.add_argument("--shape", default="c4", choices=["c4", "c2"], help="c4: R10 k=9 reads vs --ref-len contig; c2: R9 k=6 reads vs a 29 903-base genome")
     ap.add_argument("--auto-batch", action="store_true", help="leave -K / -B to the command line's own choice")
     ap.add_argument("--trace", default="", help="write the CLI's stderr (--verbose 5, SFGPU_TRACE=1) to this file")
     args = ap.parse_args()
     B.build_all()
     d = os.path.join(synth.tmpdir(), "cli_e2e")
     os.makedirs(d, exist_ok=True)
-    k = 9
+    k = 9 if args.shape == "c4" else 6
+    if args.shape == "c2":
+        args.ref_len = 29_903
     mean, stdv = synth.make_model(k)
     seq = synth.random_sequence(args.ref_len, np.random.default_rng(1))
     # a unit of at most 8288 distinct reads, its records repeated up to --reads (writing BLOW5 from Python costs
@@ -42,7 +45,7 @@ def main():
     synth.write_model_file(os.path.join(d, "model.txt"), k, mean, stdv)
     synth.write_fasta(os.path.join(d, "ref.fa"), ["chrS"], [seq])
     one = os.path.join(d, "unit.blow5")
-    synth.write_blow5(one, ids, sigs, kit="sqk-lsk114")
+    synth.write_blow5(one, ids, sigs, kit="sqk-lsk114" if k == 9 else "sqk-lsk109")
     raw = open(one, "rb").read()
     hlen = 64 + 4 + int.from_bytes(raw[64:68], "little")
     reps = max(1, round(args.reads / unit))
