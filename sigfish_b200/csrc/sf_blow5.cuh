@@ -80,17 +80,17 @@ __constant__ uint8_t sf_k_precode_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5,
 // and the inflate kernel is instruction-issue bound (ncu: issue active 70 %).
 struct sf_bits {
     const uint32_t *in;  // record start (8-byte aligned)
-    int64_t n_words;     // words that hold record bytes; words past them read as zero (never consumed by a
-                         // well-formed stream: checked at the end)
-    int64_t w;           // next word to load (hi = word w - 1, lo = word w - 2)
+    int n_words;         // words that hold record bytes; words past them read as zero (never consumed by a
+                         // well-formed stream: checked at the end).  Records are < 2 GB (checked by the caller)
+    int w;               // next word to load (hi = word w - 1, lo = word w - 2)
     uint32_t lo, hi;
     int bp;
 };
-__device__ __forceinline__ uint32_t sf_bits_word(const sf_bits &b, int64_t w) { return w < b.n_words ? __ldg(b.in + w) : 0u; }
+__device__ __forceinline__ uint32_t sf_bits_word(const sf_bits &b, int w) { return w < b.n_words ? __ldg(b.in + w) : 0u; }
 __device__ __forceinline__ void sf_bits_init(sf_bits &b, const uint8_t *rec, int64_t n_in, int skip_bits)
 {
     b.in = reinterpret_cast<const uint32_t *>(rec);
-    b.n_words = (n_in + 3) >> 2;
+    b.n_words = (int)((n_in + 3) >> 2);
     b.lo = sf_bits_word(b, 0);
     b.hi = sf_bits_word(b, 1);
     b.w = 2;
@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t sf_bits_take(sf_bits &b, int n) // n <= 16
     return v;
 }
 __device__ __forceinline__ void sf_bits_refill(sf_bits &) {} // the window always holds >= 32 bits
-__device__ __forceinline__ int64_t sf_bits_used(const sf_bits &b) { return 32 * (b.w - 2) + b.bp; }
+__device__ __forceinline__ int64_t sf_bits_used(const sf_bits &b) { return 32ll * (b.w - 2) + b.bp; }
 // has the reader run well past the end of the record?  (a damaged stream can decode the zero padding for ever)
 __device__ __forceinline__ bool sf_bits_overrun(const sf_bits &b) { return b.w > b.n_words + 4; }
 
@@ -198,9 +198,13 @@ __device__ __forceinline__ int sf_decode_sym(sf_bits &b, const uint16_t *table, 
 
 // Inflates one zlib stream with the whole warp.  out has room for cap bytes; bytes past cap are decoded but not
 // stored.  Returns the status; n_out = bytes the stream holds.
-__device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t n_in, uint8_t *out, const int64_t cap, int64_t &n_out,
+__device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t n_in, uint8_t *out, const int64_t cap64, int64_t &n_out,
                                                uint8_t *smem, const int lane)
 {
+    // positions in the output are 32-bit (a record inflates to < 2 GB: the caller checks the announced sizes, and a
+    // stream that runs past 2^31 - 2^17 bytes is refused below): the symbol loop is instruction bound, 64-bit
+    // compares and address arithmetic per literal cost a third of it
+    const unsigned cap = (unsigned)(cap64 < 0x7ffe0000ll ? cap64 : 0x7ffe0000ll);
     uint16_t *lt = reinterpret_cast<uint16_t *>(smem);
     uint16_t *dt = lt + (1 << SF_INF_LBITS);
     uint16_t *pt = dt + (1 << SF_INF_DBITS);
@@ -217,7 +221,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
         return SF_REC_EHEADER;
     sf_bits b;
     sf_bits_init(b, rec, n_in, 16); // the two header bytes are done
-    int64_t op = 0;
+    unsigned op = 0;
     int last;
     do {
         sf_bits_refill(b);
@@ -231,7 +235,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
             const uint32_t nlen = sf_bits_take(b, 16);
             if ((len ^ nlen) != 0xffffu)
                 return SF_REC_EBLOCK;
-            if ((int64_t)len > 4 * (b.n_words + 2 - b.w) + 16)
+            if ((int64_t)len > 4ll * (b.n_words + 2 - b.w) + 16 || op > 0x7ffe0000u)
                 return SF_REC_EBLOCK; // more bytes than the record has left
             for (uint32_t k = 0; k < len; k++) {
                 sf_bits_refill(b);
@@ -335,13 +339,13 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
             const int dsym = sf_decode_sym(b, dt, SF_INF_DBITS, longd, nd_long);
             if (dsym < 0 || dsym >= 30)
                 return SF_REC_ESYMBOL;
-            const int64_t dist = sf_k_dist_base[dsym] + (int64_t)sf_bits_take(b, sf_k_dist_extra[dsym]);
-            if (dist > op)
+            const unsigned dist = sf_k_dist_base[dsym] + sf_bits_take(b, sf_k_dist_extra[dsym]);
+            if (dist > op || op > 0x7ffe0000u)
                 return SF_REC_ESYMBOL;
             __syncwarp(); // the literals lane 0 stored are read by the other lanes below
             for (int k = lane; k < len; k += 32)
                 if (op + k < cap)
-                    out[op + k] = out[op - dist + (k % (int)dist)];
+                    out[op + k] = out[op - dist + ((unsigned)k % dist)];
             __syncwarp();
             op += len;
         }
@@ -359,7 +363,7 @@ __device__ __forceinline__ int sf_inflate_warp(const uint8_t *rec, const int64_t
     if (op <= cap) {
         // a = 1 + sum b_i, b = n + sum (n - i) b_i (mod 65521): partial sums per lane
         unsigned long long sa = 0, sb = 0;
-        for (int64_t i = lane; i < op; i += 32) {
+        for (unsigned i = lane; i < op; i += 32) {
             const unsigned v = out[i];
             sa += v;
             sb += (unsigned long long)(op - i) * v;

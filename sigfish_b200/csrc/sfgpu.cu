@@ -1395,6 +1395,8 @@ int sfgpu_submit_records(sfgpu_ctx *c, int32_t slot, int32_t n_reads, const uint
         const int64_t nb = record_bytes[i], ns = n_samples[i];
         if (nb < 0 || ns < 0 || ns > 0x7fffff00ll || sig_pos[i] < 0 || sig_bytes[i] < 0 || (nb > 0 && !records[i]))
             return fail(c, SFGPU_EARG, "bad record %d", i);
+        if (nb > 0x0fffffffll || (int64_t)sig_pos[i] + sig_bytes[i] > 0x7ffd0000ll) // the device decoder counts in 32 bits
+            return fail(c, SFGPU_ELIMIT, "record %d is too large for the device decoder (%lld bytes compressed)", i, (long long)nb);
         if (!record_press && (int64_t)sig_pos[i] + sig_bytes[i] > nb)
             return fail(c, SFGPU_EARG, "record %d: signal field runs past the record", i);
         rec_total += (nb + 7) & ~7ll;
