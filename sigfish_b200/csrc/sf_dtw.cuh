@@ -80,7 +80,13 @@ enum {
     SF_ST_QLEN = 24,
     SF_ST_WORDS = 32
 };
-__host__ __device__ inline int sf_smem_floats_per_warp(int R) { return 2 * SF_RING_PAIRS + 64 * R + SF_ST_WORDS; }
+// standard DTW only: the border values of lane 0 (virtual row -1: +INF, 0 in front of a segment) for every ring
+// slot, and 32 float2 of zeros that the other lanes read instead (see sf_dtw_block)
+#define SF_BORDER_FLOATS (2 * SF_RING_PAIRS + 64)
+__host__ __device__ inline int sf_smem_floats_per_warp(int R, bool std_dtw)
+{
+    return 2 * SF_RING_PAIRS + 64 * R + SF_ST_WORDS + (std_dtw ? SF_BORDER_FLOATS : 0);
+}
 // one wavefront checkpoint: L[R], dprev, botA per lane
 __host__ __device__ inline int sf_ckpt_floats(int R) { return (R + 2) * 32; }
 
@@ -135,6 +141,18 @@ __device__ __forceinline__ float sf_mask0(float v, int nz)
     asm("mul.lo.s32 %0, %1, %2;" : "=r"(ub) : "r"(__float_as_int(v)), "r"(nz)); // IMAD: fma pipe
     return __int_as_float(ub);
 }
+// standard DTW: the same multiply with the border value as addend -- lane 0 (nz = 0) gets `border`, the other lanes
+// read zeros there and keep the shuffled value.  One IMAD instead of FSETP + FSEL on the half-rate ALU pipe.
+__device__ __forceinline__ float sf_mask0_add(float v, int nz, float border)
+{
+    int ub;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(ub) : "r"(__float_as_int(v)), "r"(nz), "r"(__float_as_int(border)));
+    return __int_as_float(ub);
+}
+__device__ __forceinline__ float2 sf_border_of(const float2 v)
+{
+    return make_float2(v.x == SF_INF ? 0.0f : SF_INF, v.y == SF_INF ? 0.0f : SF_INF);
+}
 
 // 32 macro-steps = 64 reference columns.  RQ >= 0: the last query row sits in register RQ of lane lq and
 // only its two values are handed to the chunk scan (last[2s], last[2s+1]); RQ < 0: all R registers of
@@ -145,13 +163,16 @@ __device__ __forceinline__ float sf_mask0(float v, int nz)
 template <int R, bool STD, int RQ, int W = 32>
 __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R], float &botA, float &botB,
                                              float &dprev, const float2 *yb, float *last, const bool is_lq,
-                                             const int nz)
+                                             const int nz, const float2 *zb = nullptr)
 {
     const unsigned full = 0xffffffffu;
     // the 32 macro-steps are unrolled U at a time (see sf_dtw_unroll)
     constexpr int U = sf_dtw_unroll(R);
     unsigned yb_o = sf_smem_addr(yb);
     unsigned last_o = sf_smem_addr(last);
+    unsigned zb_o = 0; // STD: lane 0 reads its border values here, at the offsets of its reference events; others zeros
+    if (STD)
+        zb_o = sf_smem_addr(zb);
 #pragma unroll 1
     for (int s0 = 0; s0 < 32; s0 += U) {
 #pragma unroll
@@ -160,10 +181,9 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
         float upA = __shfl_up_sync(full, botA, 1, W);
         float upB = __shfl_up_sync(full, botB, 1, W);
         if (STD) {
-            if (!nz) { // first lane of the read
-                upA = yy.x == SF_INF ? 0.0f : SF_INF;
-                upB = yy.y == SF_INF ? 0.0f : SF_INF;
-            }
+            const float2 bb = sf_lds2(zb_o + 8 * s);
+            upA = sf_mask0_add(upA, nz, bb.x);
+            upB = sf_mask0_add(upB, nz, bb.y);
         } else {
             upA = sf_mask0(upA, nz);
             upB = sf_mask0(upB, nz);
@@ -209,6 +229,8 @@ __device__ __forceinline__ void sf_dtw_block(const float (&x)[R], float (&L)[R],
         }
     }
         yb_o += 8 * U;
+        if (STD)
+            zb_o += 8 * U;
         last_o += 8 * U * (RQ >= 0 ? 1 : R);
     }
 }
@@ -383,6 +405,7 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
 {
     const unsigned full = 0xffffffffu;
     volatile int *st = reinterpret_cast<volatile int *>(last + 64 * R);
+    float2 *bring = reinterpret_cast<float2 *>(last + 64 * R + SF_ST_WORDS); // STD only
     const sf_piece pc = a.pieces[pidx];
     const sf_group grp = a.groups[pc.gid];
     const int qlen = a.info[read].qlen;
@@ -443,6 +466,11 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
         const int cur = (b_first & 1) * 32 + lane, prv = ((b_first & 1) ^ 1) * 32 + lane;
         ring[cur] = v; ring[cur + 64] = v;
         ring[prv] = pv; ring[prv + 64] = pv;
+        if (STD) {
+            bring[cur] = bring[cur + 64] = sf_border_of(v);
+            bring[prv] = bring[prv + 64] = sf_border_of(pv);
+            bring[SF_RING_PAIRS + lane] = make_float2(0.0f, 0.0f);
+        }
     }
     if (lane == 0) {
         st[SF_ST_READ] = read;
@@ -460,11 +488,12 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
         const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
         const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
         const float2 *yb = ring + ((b & 1) ? 32 : 64) - lane;
+        const float2 *zb = lane == 0 ? bring + ((b & 1) ? 32 : 64) : bring + SF_RING_PAIRS;
 
         if (fast)
-            sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
+            sf_dtw_block<R, STD, sf_fast_rq(R)>(x, L, botA, botB, dprev, yb, last, is_lq, nz, zb);
         else
-            sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, nz);
+            sf_dtw_block<R, STD, -1>(x, L, botA, botB, dprev, yb, last, is_lq, nz, zb);
         __syncwarp();
 
         // ---- last-row chunk minima (sigfish.c:891-901): this block produced the last row of columns
@@ -521,6 +550,8 @@ __device__ __forceinline__ void sf_score_task(const sf_dtw_args &a, const int re
             const float2 v = make_float2(yn0, yn1);
             ring[slot] = v;
             ring[slot + 64] = v;
+            if (STD)
+                bring[slot] = bring[slot + 64] = sf_border_of(v);
         }
         __syncwarp();
     }
@@ -543,7 +574,7 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
     extern __shared__ float2 sf_smem2[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float2 *ring = sf_smem2 + warp * (sf_smem_floats_per_warp(R) / 2);
+    float2 *ring = sf_smem2 + warp * (sf_smem_floats_per_warp(R, STD) / 2);
     float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
     const int n_list = a.list ? *a.n_list : a.n_reads;
@@ -594,7 +625,10 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_s
 #define SF_PAIR_LANES 16
 // last-row staging of one read: 64 floats + 4 of padding, so that the two storing lanes hit different banks
 #define SF_PAIR_LAST 68
-__host__ __device__ inline int sf_pair_smem_floats_per_warp() { return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST + SF_ST_WORDS; }
+__host__ __device__ inline int sf_pair_smem_floats_per_warp(bool std_dtw)
+{
+    return 2 * SF_RING_PAIRS + 2 * SF_PAIR_LAST + SF_ST_WORDS + (std_dtw ? SF_BORDER_FLOATS : 0);
+}
 
 // One (pair of reads, piece) task.  `read` / `valid` are per half; RESUME as in sf_score_task.
 template <int R, bool STD, int RQ, bool RESUME>
@@ -604,6 +638,7 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
     constexpr int W = SF_PAIR_LANES;
     const unsigned full = 0xffffffffu;
     volatile int *st = reinterpret_cast<volatile int *>(last + 2 * SF_PAIR_LAST);
+    float2 *bring = reinterpret_cast<float2 *>(last + 2 * SF_PAIR_LAST + SF_ST_WORDS); // STD only
     const int ll = lane & (W - 1);  // lane inside the read
     const int half = lane / W;      // which read of the pair
     const int qlen = a.q_full;
@@ -651,6 +686,11 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
         const int cur = (b_first & 1) * 32 + lane, prv = ((b_first & 1) ^ 1) * 32 + lane;
         ring[cur] = v; ring[cur + 64] = v;
         ring[prv] = pv; ring[prv + 64] = pv;
+        if (STD) {
+            bring[cur] = bring[cur + 64] = sf_border_of(v);
+            bring[prv] = bring[prv + 64] = sf_border_of(pv);
+            bring[SF_RING_PAIRS + lane] = make_float2(0.0f, 0.0f);
+        }
     }
     // chunk bookkeeping is shared by the two reads (same query length, same segments); the running best is per read
     if (ll == 0) {
@@ -668,8 +708,9 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
         const float yn0 = nidx < n_pos ? __ldg(y + nidx) : SF_INF;
         const float yn1 = nidx + 1 < n_pos ? __ldg(y + nidx + 1) : SF_INF;
         const float2 *yb = ring + ((b & 1) ? 32 : 64) - ll;
+        const float2 *zb = ll == 0 ? bring + ((b & 1) ? 32 : 64) : bring + SF_RING_PAIRS;
 
-        sf_dtw_block<R, STD, RQ, W>(x, L, botA, botB, dprev, yb, last + SF_PAIR_LAST * half, is_lq, nz);
+        sf_dtw_block<R, STD, RQ, W>(x, L, botA, botB, dprev, yb, last + SF_PAIR_LAST * half, is_lq, nz, zb);
         __syncwarp();
 
         // ---- last-row chunk minima: this block produced columns p0 .. p0+63 of both reads; lane ll of a
@@ -712,6 +753,8 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
             const float2 v = make_float2(yn0, yn1);
             ring[slot] = v;
             ring[slot + 64] = v;
+            if (STD)
+                bring[slot] = bring[slot + 64] = sf_border_of(v);
         }
         __syncwarp();
     }
@@ -732,7 +775,7 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_p
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int half = lane / W;
-    float2 *ring = sf_smem2 + warp * (sf_pair_smem_floats_per_warp() / 2);
+    float2 *ring = sf_smem2 + warp * (sf_pair_smem_floats_per_warp(STD) / 2);
     float *last = reinterpret_cast<float *>(ring + SF_RING_PAIRS);
     const unsigned full = 0xffffffffu;
     const int n_list = *a.n_list;

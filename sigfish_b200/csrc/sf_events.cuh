@@ -11,9 +11,8 @@
 // The MAD trim of events.c:99-269 has no effect on the reference's results (its return value is
 // dropped at events.c:567) and is not implemented.
 //
-// One read per WARP (the sequential peak detector is the critical path of a read, so the way to go faster
-// is more reads in flight per SM, not more threads per read).  The signal is consumed in tiles of
-// SF_EV_TILE samples:
+// One read per WARP for the parallel phases, ONE warp per block for the serial phase.  The signal is consumed in
+// tiles of SF_EV_TILE samples:
 //   1. every lane loads 8 consecutive int16 samples with one 16-byte load and converts to pA;
 //   2. warp-wide fp64 scan of (x, x*x) continuing from the previous tile.  Every addition is
 //      checked with TwoSum: when all partial sums are exact the scan equals the reference's
@@ -23,18 +22,29 @@
 //      that the right-hand window is available);
 //   4. lane 0 runs the two coupled peak finders over the tile (inherently sequential), closes
 //      events as boundaries are emitted and stops the warp as soon as the query window is
-//      complete (exact: the detector is causal).
+//      complete (exact: the detector is causal).  The finder state lives in shared memory
+//      between tiles, so the parallel phases do not carry it in registers (96 registers, 5 blocks per SM).
+// Measured dead end (round 2, NOTES.md): running the detectors of all the block's reads on the lanes of ONE warp
+// (a quarter of the instructions) is slower, 4.9 - 6.7 ms against 3.3 ms per 16 384 reads: the detector is a
+// latency chain, and divergent lanes serialise it further; what hides it is many warps per SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <cfloat>
 #include "sf_types.cuh"
 
-#define SF_EV_READS_PER_BLOCK 4
+#ifndef SF_EV_READS_PER_BLOCK
+#define SF_EV_READS_PER_BLOCK 4                       // reads (= warps) per block
+#endif
+#ifndef SF_EV_MIN_BLOCKS
+#define SF_EV_MIN_BLOCKS 5                            // 96 registers; 4 - 7 blocks measured, 5 is the fastest
+#endif
 #define SF_EV_THREADS (32 * SF_EV_READS_PER_BLOCK)
 #define SF_EV_PER_THREAD 8
 #define SF_EV_TILE (32 * SF_EV_PER_THREAD)           // 256 samples per warp per tile
 #define SF_EV_LAG 32                                  // t-stat runs this far behind the scan
 #define SF_EV_KEEP 64                                 // prefix sums kept from the previous tile
+#define SF_EV_S_ROW (SF_EV_KEEP + SF_EV_TILE + 1)    // doubles per read: 2 x 321 words, lanes k hit banks 2k (mod 32)
+#define SF_EV_T_ROW (SF_EV_TILE + SF_EV_LAG)         // floats per read
 
 struct sf_ev_args {
     const int16_t *signal;      // all reads of the batch, concatenated (each read 16-byte aligned)
@@ -116,72 +126,90 @@ __device__ __forceinline__ void sf_twosum(double a, double b, double &s, int &in
     inexact |= (err != 0.0);
 }
 
-__global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_args a)
+// everything the serial phase of one read carries from tile to tile
+struct sf_ev_state {
+    sf_finder f0, f1;
+    long long npk;              // boundaries found = events closed
+    long long need_peaks;       // events needed before the read may stop: boundary index qend-1 must exist
+    long long qs;               // automatic start: index of the first event at or after the poly-A end (-1: not yet)
+    unsigned long long prev_b;  // start of the open event
+    double prev_s;              // prefix sum there
+    int stop;                   // query window complete
+    int pad;
+};
+
+__host__ __device__ inline size_t sf_events_smem_bytes()
 {
-    // per warp: prefix sums of the samples [rel, rel + KEEP + TILE]; slot j holds S[rel + j]
-    __shared__ double S_all[SF_EV_READS_PER_BLOCK][SF_EV_KEEP + SF_EV_TILE + 1];
-    __shared__ double SS_all[SF_EV_READS_PER_BLOCK][SF_EV_KEEP + SF_EV_TILE + 1];
-    __shared__ float T1_all[SF_EV_READS_PER_BLOCK][SF_EV_TILE + SF_EV_LAG];
-    __shared__ float T2_all[SF_EV_READS_PER_BLOCK][SF_EV_TILE + SF_EV_LAG];
+    return (size_t)SF_EV_READS_PER_BLOCK * (2 * SF_EV_S_ROW * sizeof(double) + 2 * SF_EV_T_ROW * sizeof(float) + sizeof(sf_ev_state)) + 16;
+}
+
+__global__ void __launch_bounds__(SF_EV_THREADS, SF_EV_MIN_BLOCKS) sf_events_kernel(const sf_ev_args a)
+{
+    constexpr int K = SF_EV_READS_PER_BLOCK;
+    // per read: prefix sums of the samples [rel, rel + KEEP + TILE] (slot j holds S[rel + j]), the two statistics of
+    // the tile, the detector state
+    extern __shared__ double sf_ev_smem[];
+    double *S_all = sf_ev_smem;
+    double *SS_all = S_all + K * SF_EV_S_ROW;
+    sf_ev_state *st_all = reinterpret_cast<sf_ev_state *>(SS_all + K * SF_EV_S_ROW);
+    float *T1_all = reinterpret_cast<float *>(st_all + K);
+    float *T2_all = T1_all + K * SF_EV_T_ROW;
 
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5;
-    const int tid = threadIdx.x & 31; // lane: the warp is the unit of work
-    const int read = blockIdx.x * SF_EV_READS_PER_BLOCK + warp;
-    if (read >= a.n_reads)
-        return;
-    double *S = S_all[warp], *SS = SS_all[warp];
-    float *T1 = T1_all[warp], *T2 = T2_all[warp];
-    const long long n = a.sig_len[read];
-    const int16_t *raw = a.signal + a.sig_off[read];
+    const int tid = threadIdx.x & 31; // lane: the warp is the unit of work of the parallel phases
+    const int read = blockIdx.x * K + warp;
+    const bool have = read < a.n_reads;
+    double *S = S_all + warp * SF_EV_S_ROW, *SS = SS_all + warp * SF_EV_S_ROW;
+    float *T1 = T1_all + warp * SF_EV_T_ROW, *T2 = T2_all + warp * SF_EV_T_ROW;
+    const long long n = have ? a.sig_len[read] : 0;
+    const int16_t *raw = a.signal + (have ? a.sig_off[read] : 0);
     const bool rna = (a.flags & SF_RNA) != 0;
     const bool from_end = (a.flags & SF_END) != 0;
     const int w1 = rna ? 7 : 3, w2 = rna ? 14 : 6;
     const float height = rna ? 1.0f : 0.2f;
-    const float unit = __fdiv_rn(a.range[read], a.digitisation[read]);
-    const float offs = a.offset[read];
+    const float unit = have ? __fdiv_rn(a.range[read], a.digitisation[read]) : 1.0f;
+    const float offs = have ? a.offset[read] : 0.0f;
     const int cap = a.ev_cap;
-    uint64_t *ev_start = a.ev_start + (size_t)read * cap;
-    float *ev_mean = a.ev_mean + (size_t)read * cap;
-    float *ev_len = a.ev_len + (size_t)read * cap;
-    // events needed before the warp may stop: boundary index qend-1 must exist
+    uint64_t *ev_start = a.ev_start + (size_t)(have ? read : 0) * cap;
+    float *ev_mean = a.ev_mean + (size_t)(have ? read : 0) * cap;
+    float *ev_len = a.ev_len + (size_t)(have ? read : 0) * cap;
     const bool autop = a.p < 0 && !a.keep_all;
-    const long long pe = autop ? a.polya_end[read] : -1; // sigfish.c:380-422
-    long long need_peaks = (from_end || a.keep_all) ? (1ll << 62) : (long long)(a.p < 0 ? 50 : a.p) + a.q;
-    if (autop && pe > 0)
-        need_peaks = 1ll << 62; // until the first event at or after the poly-A end is known
-    long long qs = -1;          // index of that event
-
-    // sequential state (lane 0 only)
-    sf_finder f0, f1;
-    f0.threshold = rna ? 2.5f : 1.4f; f1.threshold = 9.0f;
-    f0.window = w1; f1.window = w2;
-    f0.masked_to = 0; f1.masked_to = 0;
-    f0.peak_sum = 0.0; f1.peak_sum = 0.0;
-    sf_finder_reset(f0); sf_finder_reset(f1);
-    long long npk = 0;
-    unsigned long long prev_b = 0; // start of the open event
-    double prev_s = 0.0;           // prefix sum there
+    const long long n_tiles = (n + SF_EV_TILE - 1) / SF_EV_TILE;
     int sticky = 0;
-    int stop_flag = 0;
 
     if (tid == 0) {
         S[SF_EV_KEEP] = 0.0; SS[SF_EV_KEEP] = 0.0; // S[0] for the first tile (rel = -KEEP)
-    }
-    __syncwarp();
-
-    if (n <= 0) {
-        if (tid == 0) {
+        sf_ev_state z;
+        z.f0.threshold = rna ? 2.5f : 1.4f; z.f1.threshold = 9.0f;
+        z.f0.window = w1; z.f1.window = w2;
+        z.f0.masked_to = 0; z.f1.masked_to = 0;
+        z.f0.peak_sum = 0.0; z.f1.peak_sum = 0.0;
+        sf_finder_reset(z.f0); sf_finder_reset(z.f1);
+        z.npk = 0;
+        z.need_peaks = (from_end || a.keep_all) ? (1ll << 62) : (long long)(a.p < 0 ? 50 : a.p) + a.q;
+        if (autop && have && a.polya_end[read] > 0) // sigfish.c:380-422
+            z.need_peaks = 1ll << 62; // until the first event at or after the poly-A end is known
+        z.qs = -1;
+        z.prev_b = 0;
+        z.prev_s = 0.0;
+        z.stop = 0;
+        z.pad = 0;
+        st_all[warp] = z;
+        if (have && n <= 0) {
             sf_readinfo ri; ri.n_events = 0; ri.qstart = ri.qend = ri.qlen = 0; ri.status = 0; ri.start_raw = ri.end_raw = 0;
             a.info[read] = ri;
         }
-        return;
     }
+    __syncwarp();
+    if (!have || n <= 0)
+        return;
+    const long long pe = autop ? a.polya_end[read] : -1; // sigfish.c:380-422
 
-    const long long n_tiles = (n + SF_EV_TILE - 1) / SF_EV_TILE;
     for (long long tile = 0; tile < n_tiles; tile++) {
         const long long base = tile * SF_EV_TILE;  // first sample scanned in this tile
         const long long rel = base - SF_EV_KEEP;   // sample count of slot 0
+        const long long lo_pos = base - SF_EV_LAG < 0 ? 0 : base - SF_EV_LAG;
         // ---- 1+2: load, convert, scan ----
         float xs[SF_EV_PER_THREAD];
         {
@@ -255,7 +283,6 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
 
         // ---- 3: t-statistics for positions [base - LAG, hi_pos) ----
         const long long scanned = min(base + SF_EV_TILE, n); // prefix sums known up to S[scanned]
-        const long long lo_pos = base - SF_EV_LAG < 0 ? 0 : base - SF_EV_LAG;
         const long long hi_pos = (scanned >= n) ? n : base + SF_EV_TILE - SF_EV_LAG;
         for (long long i = lo_pos + tid; i < hi_pos; i += 32) {
             float t1 = 0.0f, t2 = 0.0f;
@@ -265,8 +292,13 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         }
         __syncwarp();
 
-        // ---- 4: sequential peak finders + event closing (lane 0) ----
+        // ---- 4: sequential peak finders + event closing (lane 0); the state comes from and returns to shared memory.
+        //      Inside a tile every position is a 32-bit offset from lo_pos (the 64-bit compares and adds of absolute
+        //      positions were a third of the loop's instructions). ----
         if (tid == 0) {
+            sf_ev_state z = st_all[warp];
+#ifdef SF_EV_DET64
+            sf_finder &f0 = z.f0, &f1 = z.f1;
             // the two statistics of the next position are fetched one iteration ahead: the loads do not depend on the
             // detector state, their latency would otherwise sit in every step of the serial chain
             float nx1 = T1[0], nx2 = T2[0];
@@ -306,38 +338,147 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
                     if (me.valid && ((unsigned long long)i - (unsigned long long)me.peak_pos) > me.window / 2) {
                         // boundary at peak_pos closes the open event (events.c:461-477)
                         const unsigned long long b = (unsigned long long)me.peak_pos;
-                        const float len = (float)(b - prev_b);
-                        const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(me.peak_sum, prev_s)), len);
+                        const float len = (float)(b - z.prev_b);
+                        const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(me.peak_sum, z.prev_s)), len);
                         if (!autop) {
-                            const long long slot = npk % cap;
-                            ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                            const long long slot = z.npk % cap;
+                            ev_start[slot] = z.prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
                         } else {
-                            if (npk < a.cap_a) { ev_start[npk] = prev_b; ev_mean[npk] = mean; ev_len[npk] = len; }
-                            if (qs >= 0 && npk - qs < cap - a.cap_a) {
-                                const long long slot = a.cap_a + (npk - qs);
-                                ev_start[slot] = prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                            if (z.npk < a.cap_a) { ev_start[z.npk] = z.prev_b; ev_mean[z.npk] = mean; ev_len[z.npk] = len; }
+                            if (z.qs >= 0 && z.npk - z.qs < cap - a.cap_a) {
+                                const long long slot = a.cap_a + (z.npk - z.qs);
+                                ev_start[slot] = z.prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
                             }
                         }
-                        npk++;
-                        prev_b = b; prev_s = me.peak_sum;
+                        z.npk++;
+                        z.prev_b = b; z.prev_s = me.peak_sum;
                         // the event that opens here is the first one starting at or after the poly-A end
-                        if (autop && qs < 0 && pe > 0 && b >= (unsigned long long)pe) {
-                            qs = npk;
-                            need_peaks = qs + a.q;
+                        if (autop && z.qs < 0 && pe > 0 && b >= (unsigned long long)pe) {
+                            z.qs = z.npk;
+                            z.need_peaks = z.qs + a.q;
                         }
                         me.peak_pos = -1;
                         me.peak_val = v;
                         me.valid = 0;
                     }
                 }
-                if (npk >= need_peaks) {
-                    stop_flag = 1;
+                if (z.npk >= z.need_peaks) {
+                    z.stop = 1;
                     break;
                 }
             }
+#else
+            constexpr int FAR = -(1 << 30); // a peak that far behind the tile keeps its absolute position in the state
+            const int cnt = (int)(hi_pos - lo_pos);
+            const int s_off = (int)(lo_pos - rel); // S[i - rel] = S[j + s_off]
+            // per finder, relative to lo_pos: positions <= msk are masked; pk = peak position (hp: there is a peak)
+            int msk[2], pk[2], valid[2];
+            bool hp[2];
+            float pv[2];
+            double psum[2];
+            const float thr[2] = {z.f0.threshold, z.f1.threshold};
+            const int win[2] = {w1, w2};
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                const sf_finder &me = d == 0 ? z.f0 : z.f1;
+                const long long dm = (long long)me.masked_to - lo_pos;
+                msk[d] = dm < 0 ? -1 : (int)(dm > (1 << 20) ? (1 << 20) : dm);
+                hp[d] = me.peak_pos >= 0;
+                const long long dp = me.peak_pos - lo_pos;
+                pk[d] = dp < FAR ? FAR : (int)dp;
+                pv[d] = me.peak_val;
+                valid[d] = me.valid;
+                psum[d] = me.peak_sum;
+            }
+            int slot = (int)(z.npk % cap); // ring slot of the next event (prefix_size >= 0)
+            // the two statistics of the next position are fetched one iteration ahead: the loads do not depend on the
+            // detector state, their latency would otherwise sit in every step of the serial chain
+            float nx1 = T1[0], nx2 = T2[0];
+            for (int j = 0; j < cnt; j++) {
+                const float cur1 = nx1, cur2 = nx2;
+                if (j + 1 < cnt) {
+                    nx1 = T1[j + 1];
+                    nx2 = T2[j + 1];
+                }
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    if (j <= msk[d])
+                        continue;
+                    const float v = d == 0 ? cur1 : cur2;
+                    if (!hp[d]) {
+                        if (v < pv[d]) {
+                            pv[d] = v;
+                        } else if (__fsub_rn(v, pv[d]) > height) {
+                            pv[d] = v;
+                            hp[d] = true;
+                            pk[d] = j;
+                            psum[d] = S[j + s_off];
+                        }
+                        continue;
+                    }
+                    if (v > pv[d]) {
+                        pv[d] = v;
+                        pk[d] = j;
+                        psum[d] = S[j + s_off];
+                    }
+                    if (d == 0 && pv[0] > thr[0]) { // the short finder's peak masks the long one (events.c:411-416)
+                        msk[1] = pk[0] + win[0];
+                        hp[1] = false;
+                        pv[1] = FLT_MAX;
+                        valid[1] = 0;
+                    }
+                    if (__fsub_rn(pv[d], v) > height && pv[d] > thr[d])
+                        valid[d] = 1;
+                    if (valid[d] && (j - pk[d]) > win[d] / 2) {
+                        // boundary at the peak closes the open event (events.c:461-477)
+                        const unsigned long long b = pk[d] == FAR ? (unsigned long long)(d == 0 ? z.f0.peak_pos : z.f1.peak_pos)
+                                                                  : (unsigned long long)(lo_pos + pk[d]);
+                        const float len = (float)(b - z.prev_b);
+                        const float mean = __fdiv_rn(__double2float_rn(__dsub_rn(psum[d], z.prev_s)), len);
+                        if (!autop) {
+                            ev_start[slot] = z.prev_b; ev_mean[slot] = mean; ev_len[slot] = len;
+                            slot = slot + 1 == cap ? 0 : slot + 1;
+                        } else {
+                            if (z.npk < a.cap_a) { ev_start[z.npk] = z.prev_b; ev_mean[z.npk] = mean; ev_len[z.npk] = len; }
+                            if (z.qs >= 0 && z.npk - z.qs < cap - a.cap_a) {
+                                const long long sl = a.cap_a + (z.npk - z.qs);
+                                ev_start[sl] = z.prev_b; ev_mean[sl] = mean; ev_len[sl] = len;
+                            }
+                        }
+                        z.npk++;
+                        z.prev_b = b; z.prev_s = psum[d];
+                        // the event that opens here is the first one starting at or after the poly-A end
+                        if (autop && z.qs < 0 && pe > 0 && b >= (unsigned long long)pe) {
+                            z.qs = z.npk;
+                            z.need_peaks = z.qs + a.q;
+                        }
+                        hp[d] = false;
+                        pv[d] = v;
+                        valid[d] = 0;
+                    }
+                }
+                if (z.npk >= z.need_peaks) {
+                    z.stop = 1;
+                    break;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                sf_finder &me = d == 0 ? z.f0 : z.f1;
+                me.masked_to = msk[d] < 0 ? 0ull : (unsigned long long)(lo_pos + msk[d]);
+                if (!hp[d])
+                    me.peak_pos = -1;
+                else if (pk[d] != FAR)
+                    me.peak_pos = lo_pos + pk[d]; // FAR: unchanged since the tile began
+                me.peak_val = pv[d];
+                me.valid = valid[d];
+                me.peak_sum = psum[d];
+            }
+#endif
+            st_all[warp] = z;
         }
-        stop_flag = __shfl_sync(full, stop_flag, 0);
-        if (stop_flag)
+        __syncwarp();
+        if (st_all[warp].stop)
             break;
         // keep the last KEEP+1 prefix sums for the next tile
         double ks[3], kq[3];
@@ -355,6 +496,13 @@ __global__ void __launch_bounds__(SF_EV_THREADS) sf_events_kernel(const sf_ev_ar
         }
         __syncwarp();
     }
+    // the serial phase's results (lane 0 uses them)
+    const long long npk = st_all[warp].npk;
+    long long qs = st_all[warp].qs;
+    const unsigned long long prev_b = st_all[warp].prev_b;
+    const double prev_s = st_all[warp].prev_s;
+    const int stop_flag = st_all[warp].stop;
+    __syncwarp();
 
     // ---- window + z-score + query (fp32 sums in the reference's order by lane 0; everything elementwise by the warp) ----
     sf_readinfo ri;

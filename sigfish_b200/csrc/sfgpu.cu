@@ -490,7 +490,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             SF_CUDA(c, cudaGetLastError());
             s.timing.other_launches++;
         }
-        sf_events_kernel<<<(n + SF_EV_READS_PER_BLOCK - 1) / SF_EV_READS_PER_BLOCK, SF_EV_THREADS, 0, st>>>(ea);
+        sf_events_kernel<<<(n + SF_EV_READS_PER_BLOCK - 1) / SF_EV_READS_PER_BLOCK, SF_EV_THREADS, sf_events_smem_bytes(), st>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         s.timing.other_launches++;
     }
@@ -531,8 +531,8 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         da.n_split = lv.n_split;
         da.split_first = lv.d_split_first;
         da.split_count = lv.d_split_count;
-        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(c->R);
-        const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
+        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(c->R, std_dtw);
+        const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp(std_dtw);
         const long long n_tasks = (long long)n * lv.n_pieces;
         if (n_tasks > 0x7ffffff0ll)
             return fail(c, SFGPU_ELIMIT, "batch of %d reads x %d tasks per read exceeds the task counter; use a smaller batch", n, lv.n_pieces);
@@ -1132,7 +1132,7 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             memset(&s.timing, 0, sizeof s.timing);
         }
         const bool std_dtw = (opt->flags & SFGPU_DTW) != 0;
-        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(rows);
+        const size_t smem = sizeof(float) * SF_DTW_WARPS * sf_smem_floats_per_warp(rows, std_dtw);
         int nb = 0;
         SF_DISPATCH_R(rows, std_dtw, (nb = dtw_occupancy<R, STD>(smem)));
         if (nb <= 0)
@@ -1144,6 +1144,8 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
                                                               SF_INF_WARPS * SF_INF_SMEM_WARP) == cudaSuccess && ib > 0)
                 c->inflate_blocks_per_sm = ib;
         }
+        // the event kernel keeps the prefix sums and statistics of its reads in > 48 KB of dynamic shared memory
+        SF_CUDA(c, cudaFuncSetAttribute(sf_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_events_smem_bytes()));
         c->ck_floats = sf_ckpt_floats(rows);
         // Two full-length reads per warp (16 lanes x 16 rows each) where that beats one read per warp: the pair layout
         // computes 256 rows per read whatever q is, so its useful rate falls as q/256 (measured on the 1 Mb shape:
@@ -1155,7 +1157,7 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
             c->R2 = 16;
             c->RQ2 = (opt->query_size - 1) % 16;
             c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);
-            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp();
+            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp(std_dtw);
             int pnb = 0;
             SF_DISPATCH_PAIR(c->RQ2, std_dtw, (pnb = pair_occupancy<RQ, STD>(psmem)));
             if (pnb <= 0)
@@ -1793,7 +1795,7 @@ int64_t sfgpu_event_table(sfgpu_ctx *c, const int16_t *signal, int64_t n_samples
         ea.cap_a = 0;
         ea.win_start = nullptr;
         ea.win_len = nullptr;
-        sf_events_kernel<<<1, SF_EV_THREADS>>>(ea);
+        sf_events_kernel<<<1, SF_EV_THREADS, sf_events_smem_bytes()>>>(ea);
         SF_CUDA(c, cudaGetLastError());
         SF_CUDA(c, cudaDeviceSynchronize());
         SF_CUDA(c, cudaMemcpy(&info, d_info, sizeof info, cudaMemcpyDeviceToHost));
