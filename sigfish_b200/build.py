@@ -22,8 +22,9 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",            # the reference is built without FMA contraction
     "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 
 def _newer(target: str, sources) -> bool:
@@ -46,13 +47,24 @@ def gpu_sources():
 
 
 def build_gpu(force: bool = False, verbose: bool = False) -> str:
+    """libsfgpu.so = sfgpu.cu (C-ABI + most kernels) + the sf_inst_*.cu translation units that hold the ~250
+    instantiations of the pair DTW kernel; the translation units are compiled side by side."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs = gpu_sources()
     if not force and _newer(LIB_GPU, srcs):
         return LIB_GPU
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_GPU, os.path.join(CSRC, "sfgpu.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    units = [s for s in srcs if s.endswith(".cu")]
+    objs = [os.path.join(OBJ_DIR, os.path.basename(u)[:-3] + ".o") for u in units]
+
+    def compile_unit(uo):
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", "-o", uo[1], uo[0]]
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
+        list(ex.map(compile_unit, zip(units, objs)))
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_GPU] + objs, check=True)
     return LIB_GPU
 
 

@@ -767,8 +767,13 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
     __syncwarp();
 }
 
+#ifndef SF_PAIR_MB_LO
+#define SF_PAIR_MB_LO 7
+#endif
+__host__ __device__ constexpr int sf_pair_min_blocks(int R) { return R <= 8 ? 10 : (R <= 12 ? SF_PAIR_MB_LO : 7); }
+
 template <int R, bool STD, int RQ, bool FIX = false>
-__global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_pair_kernel(const sf_dtw_args a)
+__global__ void __launch_bounds__(SF_DTW_THREADS, sf_pair_min_blocks(R)) sf_dtw_pair_kernel(const sf_dtw_args a)
 {
     constexpr int W = SF_PAIR_LANES;
     extern __shared__ float2 sf_smem2[];
@@ -819,6 +824,7 @@ __global__ void __launch_bounds__(SF_DTW_THREADS, sf_dtw_min_blocks(R)) sf_dtw_p
         asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+#ifndef SF_PAIR_INST_IMPL // the non-template kernels are compiled by sfgpu.cu only
 // Marks, for every (read, split group), the first piece whose warm front differs from the checkpoint its predecessor
 // wrote at the same boundary (atomicMin into first_bad, preset to 0x7fffffff).  One warp per (read, warm front).
 struct sf_verify_args {
@@ -913,3 +919,4 @@ __global__ void __launch_bounds__(SF_PART_THREADS) sf_partition_kernel(sf_readin
         counts[1] = base_o;
     }
 }
+#endif

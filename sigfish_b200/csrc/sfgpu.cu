@@ -28,6 +28,7 @@
 #include "sf_blow5.cuh"
 #include "sf_ref.cuh"
 #include "sf_dtw.cuh"
+#include "sf_pair_inst.cuh"
 #include "sf_trace.cuh"
 #include "sf_path.cuh"
 
@@ -305,52 +306,6 @@ cudaError_t launch_dtw_fix(const sf_dtw_args &a, int grid, size_t smem, cudaStre
     return cudaErrorInvalidValue;
 }
 
-template <int RQ, bool STD> cudaError_t launch_pair_fix(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
-{
-    if constexpr (!STD) {
-        sf_dtw_pair_kernel<16, false, RQ, true><<<grid, SF_DTW_THREADS, smem, st>>>(a);
-        return cudaGetLastError();
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int RQ, bool STD> int pair_occupancy(size_t smem)
-{
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf_dtw_pair_kernel<16, STD, RQ, false>, SF_DTW_THREADS, smem);
-    return nb;
-}
-
-// launched behind sf_dtw_score_kernel in the same stream, allowed to start once that kernel's blocks are resident
-template <int RQ, bool STD> cudaError_t launch_pair(const sf_dtw_args &a, int grid, size_t smem, cudaStream_t st)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(SF_DTW_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, sf_dtw_pair_kernel<16, STD, RQ, false>, a);
-}
-
-// the pair kernel is instantiated for every register the last query row can sit in (RQ = (q - 1) % 16), i.e. for
-// every query size in (128, 256]
-template <typename F, int... RQs> bool dispatch_pair(int rq, bool std_dtw, F &&f, std::integer_sequence<int, RQs...>)
-{
-    return ((rq == RQs && (std_dtw ? (f(std::integral_constant<int, RQs>{}, std::true_type{}), true)
-                                   : (f(std::integral_constant<int, RQs>{}, std::false_type{}), true))) || ...);
-}
-#define SF_DISPATCH_PAIR(RQ_, STD_, EXPR)                                                         \
-    dispatch_pair((RQ_), (STD_), [&](auto rq_tag_, auto std_tag_) {                               \
-        constexpr int RQ = decltype(rq_tag_)::value;                                              \
-        constexpr bool STD = decltype(std_tag_)::value;                                           \
-        EXPR;                                                                                     \
-    }, std::make_integer_sequence<int, 16>{})
-
 template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaStream_t st)
 {
     const int warps = 4;
@@ -359,20 +314,44 @@ template <int R, bool STD> cudaError_t launch_path(const sf_path_args &a, cudaSt
     return cudaGetLastError();
 }
 
-template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cudaStream_t st, bool pair)
+// the reads the pair kernel aligned (R2 rows per lane, 16 lanes per read) are traced two per warp
+template <int R2, bool STD> cudaError_t launch_trace_pair(const sf_trace_args &a, cudaStream_t st)
+{
+    const int warps = 4;
+    const int units = (a.n_reads + 1) / 2;
+    sf_trace_pair_kernel<R2, STD><<<(units + warps - 1) / warps, warps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cudaStream_t st, int r2)
 {
     const int warps = 4;
     const int grid = (a.n_reads + warps - 1) / warps;
-    if constexpr (R >= 5 && R <= 8) { // pairing exists for 128 < q <= 256, i.e. R = 5..8 in the warp-per-read layout
-        if (pair) {
-            // the reads the pair kernel aligned are traced two per warp; the others by the general kernel
+    if constexpr (R >= 3 && R <= 8) { // pairing exists for 64 < q <= 256, i.e. R = 3..8 in the warp-per-read layout
+        if (r2 > 0) {
+            // the paired reads are skipped by the general kernel (its third parameter only says that there are any)
             sf_trace_kernel<R, STD, 16><<<grid, warps * 32, 0, st>>>(a);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess)
                 return e;
-            const int units = (a.n_reads + 1) / 2;
-            sf_trace_pair_kernel<16, STD><<<(units + warps - 1) / warps, warps * 32, 0, st>>>(a);
-            return cudaGetLastError();
+            if (r2 == 16)
+                return launch_trace_pair<16, STD>(a, st);
+            if constexpr (!STD) {
+                switch (r2) {
+                case 5: return launch_trace_pair<5, false>(a, st);
+                case 6: return launch_trace_pair<6, false>(a, st);
+                case 7: return launch_trace_pair<7, false>(a, st);
+                case 8: return launch_trace_pair<8, false>(a, st);
+                case 9: return launch_trace_pair<9, false>(a, st);
+                case 10: return launch_trace_pair<10, false>(a, st);
+                case 11: return launch_trace_pair<11, false>(a, st);
+                case 12: return launch_trace_pair<12, false>(a, st);
+                case 13: return launch_trace_pair<13, false>(a, st);
+                case 14: return launch_trace_pair<14, false>(a, st);
+                case 15: return launch_trace_pair<15, false>(a, st);
+                }
+            }
+            return cudaErrorInvalidValue;
         }
     }
     sf_trace_kernel<R, STD, 0><<<grid, warps * 32, 0, st>>>(a);
@@ -560,9 +539,9 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             s.timing.dtw_launches++;
             pa.list = s.d_list_full;
             pa.n_list = s.d_counts;
-            e = cudaErrorInvalidValue;
-            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair<RQ, STD>(pa, pgrid, psmem, st)));
-            SF_CUDA(c, e);
+            sf_pair_op op = {SF_PAIR_LAUNCH, &pa, pgrid, psmem, st, 0, cudaErrorInvalidValue};
+            sf_pair_run(c->R2, c->RQ2, std_dtw, op);
+            SF_CUDA(c, op.err);
         } else {
             SF_DISPATCH_R(c->R, std_dtw, (e = launch_dtw<R, STD>(oa, grid, smem, st)));
             SF_CUDA(c, e);
@@ -601,10 +580,11 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
             SF_CUDA(c, e);
             s.timing.dtw_launches++;
             if (c->R2 > 0) {
-                e = cudaErrorInvalidValue;
-                SF_DISPATCH_PAIR(c->RQ2, std_dtw, (e = launch_pair_fix<RQ, STD>(
-                    pa, (int)std::max<long long>(1, std::min<long long>(fwant, (long long)c->sm_count * c->pair_blocks_per_sm)), psmem, st)));
-                SF_CUDA(c, e);
+                sf_pair_op op = {SF_PAIR_LAUNCH_FIX, &pa,
+                                 (int)std::max<long long>(1, std::min<long long>(fwant, (long long)c->sm_count * c->pair_blocks_per_sm)),
+                                 psmem, st, 0, cudaErrorInvalidValue};
+                sf_pair_run(c->R2, c->RQ2, std_dtw, op);
+                SF_CUDA(c, op.err);
                 s.timing.dtw_launches++;
             }
         }
@@ -632,7 +612,7 @@ int run_stages(sfgpu_ctx *c, sf_slot &s, bool with_h2d, bool with_events = true)
         ta.hits = s.d_hits;
         ta.min_window = c->min_window;
         cudaError_t e = cudaErrorInvalidValue;
-        SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st, c->R2 > 0)));
+        SF_DISPATCH_R(c->R, std_dtw, (e = launch_trace<R, STD>(ta, st, c->R2)));
         SF_CUDA(c, e);
         s.timing.other_launches += c->R2 > 0 ? 2 : 1;
     }
@@ -1147,22 +1127,30 @@ int sfgpu_create(sfgpu_ctx **out, const sfgpu_opt_t *opt, const float *level_mea
         // the event kernel keeps the prefix sums and statistics of its reads in > 48 KB of dynamic shared memory
         SF_CUDA(c, cudaFuncSetAttribute(sf_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf_events_smem_bytes()));
         c->ck_floats = sf_ckpt_floats(rows);
-        // Two full-length reads per warp (16 lanes x 16 rows each) where that beats one read per warp: the pair layout
-        // computes 256 rows per read whatever q is, so its useful rate falls as q/256 (measured on the 1 Mb shape:
-        // q = 256 8.68, 250 8.37, 200 6.62, 130 4.22 TCUPS), while one read per warp pads only up to the next
-        // multiple of 32 rows at ~7 TCUPS.  The pair layout wins for 192 < q <= 256 (reserved[3]: 1 = pairing off,
-        // 2 = pairing for every 128 < q <= 256, used by the tests to reach every instantiation).
-        const int pair_from = opt->reserved[3] == 2 ? 128 : 192;
-        if (opt->query_size > pair_from && opt->query_size <= 256 && opt->reserved[3] != 1) {
-            c->R2 = 16;
-            c->RQ2 = (opt->query_size - 1) % 16;
-            c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);
-            const size_t psmem = sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp(std_dtw);
-            int pnb = 0;
-            SF_DISPATCH_PAIR(c->RQ2, std_dtw, (pnb = pair_occupancy<RQ, STD>(psmem)));
-            if (pnb <= 0)
-                return fail(c, SFGPU_ECUDA, "pair DTW kernel does not fit on the device");
-            c->pair_blocks_per_sm = pnb;
+        // Two full-length reads per warp (16 lanes x R2 rows each, R2 = ceil(q / 16)) for every 64 < q <= 256: the
+        // per-macro-step overheads are shared by twice the cells, and at most 15 rows per read are padding.  Round 2
+        // had only R2 = 16 (useful rate falling as q/256: q = 256 8.68, 250 8.37, 200 6.62, 130 4.22 TCUPS on the 1 Mb
+        // shape) and used it for 192 < q <= 256; --dtw-std still has only that instantiation.  reserved[3]: 1 =
+        // pairing off, 2 = pairing for every 128 < q <= 256 also with --dtw-std (tests).
+        {
+            const int q = opt->query_size;
+            int r2 = 0;
+            if (q > 64 && q <= 256 && opt->reserved[3] != 1) {
+                if (!std_dtw)
+                    r2 = (q + SF_PAIR_LANES - 1) / SF_PAIR_LANES;
+                else if (q > 192 || (q > 128 && opt->reserved[3] == 2))
+                    r2 = 16;
+            }
+            if (r2 > 0 && sf_pair_exists(r2, std_dtw)) {
+                c->R2 = r2;
+                c->RQ2 = (q - 1) % r2;
+                c->ck_floats = std::max(c->ck_floats, (c->R2 + 2) * SF_PAIR_LANES);
+                sf_pair_op op = {SF_PAIR_OCCUPANCY, nullptr, 0, sizeof(float) * SF_DTW_WARPS * sf_pair_smem_floats_per_warp(std_dtw),
+                                 nullptr, 0, cudaErrorInvalidValue};
+                if (!sf_pair_run(c->R2, c->RQ2, std_dtw, op) || op.err != cudaSuccess || op.blocks_per_sm <= 0)
+                    return fail(c, SFGPU_ECUDA, "pair DTW kernel does not fit on the device (R2=%d, RQ=%d)", c->R2, c->RQ2);
+                c->pair_blocks_per_sm = op.blocks_per_sm;
+            }
         }
         return SFGPU_OK;
     }();

@@ -760,9 +760,10 @@ def test_slow_and_fast_reads_in_one_batch():
     ctx.close()
 
 
-# query sizes in (128, 256] that put the last query row in register 0, 1, ... 15 of its lane: one per instantiation
-# of the pair kernel
-_PAIR_Q = [129, 146, 163, 180, 197, 214, 231, 248, 137, 250, 155, 172, 189, 206, 223, 256]
+# the pair kernel holds R2 = ceil(q / 16) rows per lane and is instantiated for every register RQ = (q - 1) % R2 the
+# last query row can sit in.  Here: every RQ of R2 = 16 (240 < q <= 256), and the first, a middle and the last RQ of
+# R2 = 5 .. 15 (64 < q <= 240); test_pair_layout_every_query_size below visits all the others.
+_PAIR_Q = list(range(241, 257)) + [q for r2 in range(5, 16) for q in (16 * (r2 - 1) + 1, 16 * (r2 - 1) + 8, 16 * r2)]
 
 
 @pytest.mark.parametrize("q,std", [(q, False) for q in _PAIR_Q] + [(q, True) for q in (197, 250, 256)])
@@ -781,7 +782,7 @@ def test_paired_and_unpaired_layouts_agree(q, std):
         order = rng.permutation(len(qlens))
         queries = [_rand_arrays(rng, [qlens[j]], 2)[0] for j in order]
         outs = []
-        for nopair in (2, True):  # 2: pair whatever the query size (the default pairs only 192 < q <= 256)
+        for nopair in (2, True):  # 2: pair whatever the query size (--dtw-std pairs only 192 < q <= 256 by default)
             for ck, win in ((0, 0), (128, 1)):
                 ctx = capi.Context(model(5), 5, flags=flags, query_size=q, ck_min_cols=ck, min_window=win, no_pairing=nopair)
                 ctx.set_ref_events(fwd, rev)
@@ -797,6 +798,31 @@ def test_paired_and_unpaired_layouts_agree(q, std):
             assert g["rid"] == o.rid and "+-"[g["strand"]] == o.strand.decode(), tag
             assert bits(g["score"]) == bits(o.score) and bits(g["score2"]) == bits(o.score2), tag
             assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), tag
+    oref.close()
+
+
+def test_pair_layout_every_query_size():
+    """one small case per instantiation of sf_dtw_pair_kernel<R2, false, RQ> and sf_trace_pair_kernel<R2>: every
+    64 < q <= 256, full-length reads (odd count) + ragged ones, checkpoints and split pieces on, against the oracle"""
+    rng = np.random.default_rng(77)
+    lens = [int(x) for x in rng.integers(1, 500, size=5)] + [3000, 700]
+    fwd = _rand_arrays(rng, lens, 2)
+    rev = _rand_arrays(rng, lens, 2)
+    oref = H.OracleEventRef(fwd, rev)
+    for q in range(65, 257):
+        qlens = [q, q, q - 1, q, q // 3]
+        queries = _rand_arrays(rng, qlens, 2 if q % 2 else 0)
+        ctx = capi.Context(model(5), 5, query_size=q, ck_min_cols=128, min_window=1, piece_periods=2, warm_blocks=9)
+        ctx.set_ref_events(fwd, rev)
+        got = ctx.align_queries(queries)
+        assert ctx.timing(0).dtw_launches >= 2, q  # the pair kernel ran
+        ctx.close()
+        for i, x in enumerate(queries):
+            o = oref.align(x, 0)
+            g = got[i]
+            assert (g["rid"], "+-"[g["strand"]]) == (o.rid, o.strand.decode()), (q, i)
+            assert bits(g["score"]) == bits(o.score) and bits(g["score2"]) == bits(o.score2), (q, i)
+            assert (g["pos_st"], g["pos_end"]) == (o.raw_pos_st, o.raw_pos_end), (q, i)
     oref.close()
 
 

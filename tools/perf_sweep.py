@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-stage device timings of the hot path on the workload shapes of BASELINE.json (development aid; the
-judged numbers come from bench.py).  Usage: python tools/perf_sweep.py [c2] [c4] [c5] [--reads N] [--waves N] [-q Q] [--no-pair] [--ragged N]"""
+judged numbers come from bench.py).  Usage: python tools/perf_sweep.py [c2] [c4] [c5] [--reads N] [--waves N] [-q Q] [--no-pair] [--ragged N] [--min-window COLS] [--only-std]"""
 import os
 import sys
 import time
@@ -43,13 +43,14 @@ def main():
         q = int(sys.argv[sys.argv.index("-q") + 1])
     nopair = "--no-pair" in sys.argv
     waves = int(sys.argv[sys.argv.index("--waves") + 1]) if "--waves" in sys.argv else 0
+    minwin = int(sys.argv[sys.argv.index("--min-window") + 1]) if "--min-window" in sys.argv else 0
     rng = np.random.default_rng(3)
     if "c2" in which:  # R9 DNA vs a 30 kb genome, both strands
         k = 6
         lm, _ = synth.make_model(k)
         seq = synth.random_sequence(29903, rng)
         sigs, _ = synth.simulate_reads([seq], k, lm, n_reads, seed=5, bases_per_read=450)
-        ctx = capi.Context(lm, k, no_pairing=nopair)
+        ctx = capi.Context(lm, k, query_size=q, no_pairing=nopair, min_window=minwin)
         ctx.set_ref([seq])
         run(f"C2 30kb DNA q250{' nopair' if nopair else ''}", ctx, sigs, [synth.DNA_SCALING] * len(sigs))
         ctx.close()
@@ -57,7 +58,7 @@ def main():
         k = 9
         lm, _ = synth.make_model(k)
         seq = synth.random_sequence(1_000_000, rng)
-        ctx = capi.Context(lm, k, query_size=q, no_pairing=nopair)
+        ctx = capi.Context(lm, k, query_size=q, no_pairing=nopair, min_window=minwin)
         ctx.set_ref([seq])
         if waves:
             n_reads = waves * ctx.wave_reads
@@ -73,8 +74,11 @@ def main():
         n_tx = 5000
         seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(400, 4000, size=n_tx)]
         sigs, _ = synth.simulate_reads(seqs, k, lm, min(n_reads, 1024), seed=7, rna=True, bases_per_read=max(420, q + 450))
-        for flags, nm in ((capi.SFGPU_RNA | capi.SFGPU_INV, "C5 5k transcripts inv"), (capi.SFGPU_RNA, "C5 5k transcripts"),
-                          (capi.SFGPU_RNA | capi.SFGPU_DTW, "C5 5k transcripts dtw-std")):
+        variants = ((capi.SFGPU_RNA | capi.SFGPU_INV, "C5 5k transcripts inv"), (capi.SFGPU_RNA, "C5 5k transcripts"),
+                    (capi.SFGPU_RNA | capi.SFGPU_DTW, "C5 5k transcripts dtw-std"))
+        if "--only-std" in sys.argv:
+            variants = variants[2:]
+        for flags, nm in variants:
             ctx = capi.Context(lm, k, flags=flags, pore=2, query_size=q, no_pairing=nopair)
             ctx.set_ref(seqs)
             run(nm, ctx, sigs, [synth.RNA_SCALING] * len(sigs))
