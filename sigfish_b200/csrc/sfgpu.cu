@@ -173,7 +173,7 @@ int fail(sfgpu_ctx *c, int code, const char *fmt, ...)
                         cudaGetErrorString(e_));                                                  \
     } while (0)
 
-const int kRows[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+const int kRows[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 24, 32};
 
 int pick_rows(int q)
 {
@@ -361,7 +361,7 @@ template <int R, bool STD> cudaError_t launch_trace(const sf_trace_args &a, cuda
 // Calls f(integral_constant<int, R>, bool_constant<STD>) for the instantiated register-tile height equal to
 // `rows` (kRows) and the recurrence variant; returns false when `rows` is not instantiated.
 template <int... Rs> struct sf_row_list {};
-using sf_rows = sf_row_list<1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32>;
+using sf_rows = sf_row_list<1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 24, 32>;
 
 template <typename F, int... Rs> bool dispatch_rows(int rows, bool std_dtw, F &&f, sf_row_list<Rs...>)
 {

@@ -576,9 +576,9 @@ def test_many_short_references_more_groups_than_lanes():
     ctx.close()
 
 
-@pytest.mark.parametrize("q", [10, 40, 90, 128, 150, 180, 200, 256, 320, 380, 512, 600, 760, 1000, 1024])
+@pytest.mark.parametrize("q", [10, 40, 90, 128, 150, 180, 200, 256, 270, 320, 340, 380, 410, 440, 470, 512, 600, 760, 1000, 1024])
 def test_dtw_every_register_tile_height(q):
-    """one case per template instantiation of the DTW / trace kernels (R = 1,2,3,4,5,6,7,8,10,12,16,20,24,32):
+    """one case per template instantiation of the DTW / trace kernels (R = 1 .. 16, 20, 24, 32):
     subsequence and standard DTW, full-length and ragged queries, checkpoints on"""
     rng = np.random.default_rng(5000 + q)
     lens = [int(x) for x in rng.integers(1, 700, size=4)] + [2 * q + 37, 2500]
