@@ -728,6 +728,77 @@ static char *sam_str(const aln_t *aln, const sfgpu_result_t *r, const uint8_t *m
     return b.s;
 }
 
+/* ---- per-read epilogue of a collected batch ---- */
+#define SF_EPI_CHUNK 512
+typedef struct {
+    core_t *core;
+    db_t *db;
+    int32_t *next;
+    int64_t ignored, too_short, prefix_fail;
+} epi_arg_t;
+
+static void epilogue_read(core_t *core, db_t *db, int i, epi_arg_t *cnt)
+{
+    const refsynth_t *ref = core->ref;
+    {
+        const sfgpu_result_t *r = &db->res[i];
+        db->out[i] = NULL;
+        if (r->status & 1)
+            cnt->ignored++;
+        if (r->status & 2)
+            cnt->too_short++;
+        if (r->status & 16)
+            cnt->prefix_fail++;
+        /* no hit (only possible for degenerate queries, e.g. a constant signal whose z-score is NaN: the
+         * reference's behaviour is undefined there, SURVEY F9): print nothing */
+        if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0 || r->pos_st < 0 || r->pos_end < 0)
+            return;
+        /* src/sigfish.c:969-985 */
+        aln_t *a = &db->aln[i];
+        a->score = r->score;
+        a->score2 = r->score2;
+        a->rid = r->rid;
+        a->d = r->strand ? '-' : '+';
+        const int32_t rlen = ref->ref_lengths[r->rid];
+        a->pos_st = r->strand ? rlen - r->pos_end : r->pos_st;
+        a->pos_end = r->strand ? rlen - r->pos_st : r->pos_end;
+        a->pos_st += ref->ref_st_offset[r->rid];
+        a->pos_end += ref->ref_st_offset[r->rid];
+        const float ratio = 500 * (a->score2 - a->score) / a->score;
+        int32_t mq = to_int_like_x86(round((double)ratio));
+        if (mq > 60)
+            mq = 60;
+        a->mapq = (uint8_t)mq;
+        /* src/sigfish.c:800-807: query_size = (qend-1) - qstart */
+        const uint64_t query_size = (uint64_t)(r->qend - 1) - (uint64_t)r->qstart;
+        if (core->opt.flag & SIGFISH_SAM) {
+            if (db->n_moves[i] < 0)
+                return;
+            const int q = core->opt.query_size;
+            db->out[i] = sam_str(a, r, db->moves + db->move_off[i], db->n_moves[i], db->win_start + (size_t)i * q,
+                                 db->win_len + (size_t)i * q, db->rec[i].read_id, ref->ref_names[r->rid],
+                                 (core->opt.flag & SIGFISH_RNA) != 0);
+        } else {
+            db->out[i] = paf_str(a, db->rec[i].read_id, ref->ref_names[r->rid], r->start_raw, r->end_raw, query_size,
+                                 db->rec[i].len_raw_signal, (uint64_t)ref->ref_seq_lengths[r->rid]);
+        }
+    }
+}
+
+static void *epilogue_worker(void *p)
+{
+    epi_arg_t *a = (epi_arg_t *)p;
+    for (;;) {
+        const int32_t b = __sync_fetch_and_add(a->next, SF_EPI_CHUNK);
+        if (b >= a->db->n_rec)
+            break;
+        const int32_t e = b + SF_EPI_CHUNK < a->db->n_rec ? b + SF_EPI_CHUNK : a->db->n_rec;
+        for (int32_t i = b; i < e; i++)
+            epilogue_read(a->core, a->db, i, a);
+    }
+    return NULL;
+}
+
 void collect_db(core_t *core, db_t *db)
 {
     if (!db->submitted)
@@ -796,49 +867,36 @@ void collect_db(core_t *core, db_t *db)
         }
     }
     db->submitted = 0;
-    const refsynth_t *ref = core->ref;
-    for (int i = 0; i < db->n_rec; i++) {
-        const sfgpu_result_t *r = &db->res[i];
-        db->out[i] = NULL;
-        if (r->status & 1)
-            db->ignored++;
-        if (r->status & 2)
-            db->too_short++;
-        if (r->status & 16)
-            db->prefix_fail++;
-        /* no hit (only possible for degenerate queries, e.g. a constant signal whose z-score is NaN: the
-         * reference's behaviour is undefined there, SURVEY F9): print nothing */
-        if (db->rec[i].len_raw_signal == 0 || r->qlen <= 0 || r->rid < 0 || r->pos_st < 0 || r->pos_end < 0)
-            continue;
-        /* src/sigfish.c:969-985 */
-        aln_t *a = &db->aln[i];
-        a->score = r->score;
-        a->score2 = r->score2;
-        a->rid = r->rid;
-        a->d = r->strand ? '-' : '+';
-        const int32_t rlen = ref->ref_lengths[r->rid];
-        a->pos_st = r->strand ? rlen - r->pos_end : r->pos_st;
-        a->pos_end = r->strand ? rlen - r->pos_st : r->pos_end;
-        a->pos_st += ref->ref_st_offset[r->rid];
-        a->pos_end += ref->ref_st_offset[r->rid];
-        const float ratio = 500 * (a->score2 - a->score) / a->score;
-        int32_t mq = to_int_like_x86(round((double)ratio));
-        if (mq > 60)
-            mq = 60;
-        a->mapq = (uint8_t)mq;
-        /* src/sigfish.c:800-807: query_size = (qend-1) - qstart */
-        const uint64_t query_size = (uint64_t)(r->qend - 1) - (uint64_t)r->qstart;
-        if (core->opt.flag & SIGFISH_SAM) {
-            if (db->n_moves[i] < 0)
-                continue;
-            const int q = core->opt.query_size;
-            db->out[i] = sam_str(a, r, db->moves + db->move_off[i], db->n_moves[i], db->win_start + (size_t)i * q,
-                                 db->win_len + (size_t)i * q, db->rec[i].read_id, ref->ref_names[r->rid],
-                                 (core->opt.flag & SIGFISH_RNA) != 0);
-        } else {
-            db->out[i] = paf_str(a, db->rec[i].read_id, ref->ref_names[r->rid], r->start_raw, r->end_raw, query_size,
-                                 db->rec[i].len_raw_signal, (uint64_t)ref->ref_seq_lengths[r->rid]);
-        }
+    /* the epilogue of the reads (strand flip, offsets, MAPQ, PAF / SAM text) on the -t worker threads, as the
+     * reference does it inside work_db(); chunks of reads are claimed from a shared counter, db->out[] keeps the order */
+    int nt = core->opt.num_thread < 1 ? 1 : core->opt.num_thread;
+    if (nt > 32)
+        nt = 32;
+    if (db->n_rec < 2 * SF_EPI_CHUNK)
+        nt = 1;
+    int32_t next = 0;
+    epi_arg_t args[32];
+    pthread_t tid[32];
+    for (int t = 0; t < nt; t++) {
+        args[t].core = core;
+        args[t].db = db;
+        args[t].next = &next;
+        args[t].ignored = args[t].too_short = args[t].prefix_fail = 0;
+    }
+    if (nt == 1) {
+        epilogue_worker(&args[0]);
+    } else {
+        for (int t = 0; t < nt; t++)
+            if (pthread_create(&tid[t], NULL, epilogue_worker, &args[t])) {
+                SF_FATAL("%s", "pthread_create failed");
+            }
+        for (int t = 0; t < nt; t++)
+            pthread_join(tid[t], NULL);
+    }
+    for (int t = 0; t < nt; t++) {
+        db->ignored += args[t].ignored;
+        db->too_short += args[t].too_short;
+        db->prefix_fail += args[t].prefix_fail;
     }
 }
 
