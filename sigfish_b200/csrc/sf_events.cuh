@@ -126,6 +126,28 @@ __device__ __forceinline__ void sf_twosum(double a, double b, double &s, int &in
     inexact |= (err != 0.0);
 }
 
+// Shared-memory reads of the serial loop go through 32-bit shared addresses made opaque to the compiler: it otherwise
+// re-derives the buffer addresses (and the loop bound) from their parts in every iteration -- half of the loop's
+// instructions -- to save registers.
+__device__ __forceinline__ unsigned sf_ev_saddr(const void *p)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+template <int OFF> __device__ __forceinline__ float sf_ev_lds(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ double sf_ev_lds64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+
 // everything the serial phase of one read carries from tile to tile
 struct sf_ev_state {
     sf_finder f0, f1;
@@ -391,15 +413,25 @@ __global__ void __launch_bounds__(SF_EV_THREADS, SF_EV_MIN_BLOCKS) sf_events_ker
                 psum[d] = me.peak_sum;
             }
             int slot = (int)(z.npk % cap); // ring slot of the next event (prefix_size >= 0)
+            int cnt_o = cnt;
+            asm volatile("" : "+r"(cnt_o));
+            // loop constants held in registers (otherwise re-selected from the RNA flag at every use)
+            float height_o = height;
+            int half0 = win[0] / 2, half1 = win[1] / 2;
+            asm volatile("" : "+f"(height_o), "+r"(half0), "+r"(half1));
+            unsigned ta = sf_ev_saddr(T1);               // T2 sits K rows behind T1
+            constexpr int T2_OFF = K * SF_EV_T_ROW * (int)sizeof(float);
+            const unsigned sa = sf_ev_saddr(S + s_off);  // prefix sum at position j: sa + 8 j
             // the two statistics of the next position are fetched one iteration ahead: the loads do not depend on the
-            // detector state, their latency would otherwise sit in every step of the serial chain
-            float nx1 = T1[0], nx2 = T2[0];
-            for (int j = 0; j < cnt; j++) {
+            // detector state, their latency would otherwise sit in every step of the serial chain (the fetch past the
+            // last position reads a slot nobody uses: the rows are followed by the next row or the pad of the buffer)
+            float nx1 = sf_ev_lds<0>(ta), nx2 = sf_ev_lds<T2_OFF>(ta);
+            for (int j = 0; j < cnt_o; j++) {
                 const float cur1 = nx1, cur2 = nx2;
-                if (j + 1 < cnt) {
-                    nx1 = T1[j + 1];
-                    nx2 = T2[j + 1];
-                }
+                ta += 4;
+                nx1 = sf_ev_lds<0>(ta);
+                nx2 = sf_ev_lds<T2_OFF>(ta);
+                bool closed = false;
 #pragma unroll
                 for (int d = 0; d < 2; d++) {
                     if (j <= msk[d])
@@ -408,18 +440,18 @@ __global__ void __launch_bounds__(SF_EV_THREADS, SF_EV_MIN_BLOCKS) sf_events_ker
                     if (!hp[d]) {
                         if (v < pv[d]) {
                             pv[d] = v;
-                        } else if (__fsub_rn(v, pv[d]) > height) {
+                        } else if (__fsub_rn(v, pv[d]) > height_o) {
                             pv[d] = v;
                             hp[d] = true;
                             pk[d] = j;
-                            psum[d] = S[j + s_off];
+                            psum[d] = sf_ev_lds64(sa + 8 * j);
                         }
                         continue;
                     }
                     if (v > pv[d]) {
                         pv[d] = v;
                         pk[d] = j;
-                        psum[d] = S[j + s_off];
+                        psum[d] = sf_ev_lds64(sa + 8 * j);
                     }
                     if (d == 0 && pv[0] > thr[0]) { // the short finder's peak masks the long one (events.c:411-416)
                         msk[1] = pk[0] + win[0];
@@ -427,9 +459,9 @@ __global__ void __launch_bounds__(SF_EV_THREADS, SF_EV_MIN_BLOCKS) sf_events_ker
                         pv[1] = FLT_MAX;
                         valid[1] = 0;
                     }
-                    if (__fsub_rn(pv[d], v) > height && pv[d] > thr[d])
+                    if (__fsub_rn(pv[d], v) > height_o && pv[d] > thr[d])
                         valid[d] = 1;
-                    if (valid[d] && (j - pk[d]) > win[d] / 2) {
+                    if (valid[d] && (j - pk[d]) > (d == 0 ? half0 : half1)) {
                         // boundary at the peak closes the open event (events.c:461-477)
                         const unsigned long long b = pk[d] == FAR ? (unsigned long long)(d == 0 ? z.f0.peak_pos : z.f1.peak_pos)
                                                                   : (unsigned long long)(lo_pos + pk[d]);
@@ -455,9 +487,11 @@ __global__ void __launch_bounds__(SF_EV_THREADS, SF_EV_MIN_BLOCKS) sf_events_ker
                         hp[d] = false;
                         pv[d] = v;
                         valid[d] = 0;
+                        closed = true;
                     }
                 }
-                if (z.npk >= z.need_peaks) {
+                // the number of events only changes when one closes
+                if (closed && z.npk >= z.need_peaks) {
                     z.stop = 1;
                     break;
                 }
