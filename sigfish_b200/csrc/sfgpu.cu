@@ -786,7 +786,16 @@ int layout_ref(sfgpu_ctx *c, int32_t num_ref, const int32_t *rlens, bool has_rev
     for (int s = 0; s < c->n_seg; s++)
         if (c->segs[s].rlen > c->ck_min_cols)
             long_cols += c->segs[s].rlen + 1;
-    const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, long_cols / 512);
+    // SFGPU_CHECKPOINTS_PER_READ in the environment (16 .. 4096, default 512) trades memory against the length of the
+    // start-coordinate pass: 128 = 0.17 MB per read for 1.7 % of the throughput on the 1 Mb shape, 64 = 0.08 MB for 3.1 %
+    // (profiles/r02_checkpoint_density_knob.txt)
+    int64_t ck_target = 512;
+    if (const char *e = getenv("SFGPU_CHECKPOINTS_PER_READ")) {
+        const long v = strtol(e, nullptr, 10);
+        if (v >= 16 && v <= 4096)
+            ck_target = v;
+    }
+    const int64_t cols_per = std::max<int64_t>(c->ck_min_cols / 4, long_cols / ck_target);
     c->groups.clear();
     c->seg_group.assign(c->n_seg, 0);
     int s0 = 0;

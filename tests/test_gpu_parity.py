@@ -826,6 +826,35 @@ def test_pair_layout_every_query_size():
     oref.close()
 
 
+def test_sparse_checkpoints_knob(monkeypatch):
+    """SFGPU_CHECKPOINTS_PER_READ = 32: 16 x fewer wavefront checkpoints (the start-coordinate pass then recomputes
+    longer windows, the pieces of split segments get longer): the same bytes as the default spacing, and the oracle's
+    answer on a sample"""
+    k = 6
+    lm = model(k)
+    rng = np.random.default_rng(31)
+    seq = synth.random_sequence(300_000, rng)
+    sigs, truth = synth.simulate_reads([seq], k, lm, 96, seed=5, bases_per_read=450)
+    sc = [synth.DNA_SCALING] * len(sigs)
+    ctx = capi.Context(lm, k)
+    ctx.set_ref([seq])
+    want = ctx.map_batch(sigs, sc)
+    dense = ctx.timing(0).tasks_per_read
+    ctx.close()
+    monkeypatch.setenv("SFGPU_CHECKPOINTS_PER_READ", "32")
+    ctx = capi.Context(lm, k)
+    ctx.set_ref([seq])
+    got = ctx.map_batch(sigs, sc)
+    assert ctx.timing(0).tasks_per_read <= dense
+    ctx.close()
+    assert got.tobytes() == want.tobytes()
+    ref = H.OracleRef([seq], lm, k, 0, 250)
+    for i in (0, 50):
+        o = H.orc_map(ref, sigs[i], 8192.0, 10.0, 1402.882, 0, 250, 50)
+        assert_hit_equal(got[i], o, ("sparse", i), 0, 250, 50)
+    ref.close()
+
+
 def test_several_long_contigs_share_the_checkpoint_budget():
     """the checkpoint period is set by the total length of the long segments (~512 checkpoints per read whatever
     the genome size): six 40 kb contigs, both strands, production settings, every read against the oracle"""
