@@ -769,7 +769,8 @@ __device__ __forceinline__ void sf_pair_task(const sf_dtw_args &a, const int rea
 
 // resident blocks per SM of the pair kernel (measured on the 1 Mb shape, profiles/r02_pair_rows_follow_q.txt and
 // r02_pair_blocks_per_sm_ab.txt: 8 blocks of 64 registers against 7 of 72 are +1.9 % at R = 10, +2.7 % at R = 12, +1.9 %
-// at R = 13, but -3.6 % at R = 9, -2.2 % at R = 15 and -1.7 % at R = 16)
+// at R = 13, but -3.6 % at R = 9, -2.2 % at R = 15 and -1.7 % at R = 16; 6 blocks of 80 registers: +0.7 % at R = 16 (inside
+// the box-to-box noise), -2.7 % at R = 15)
 __host__ __device__ constexpr int sf_pair_min_blocks(int R) { return R <= 8 ? 10 : (R == 9 ? 7 : (R <= 13 ? 8 : 7)); }
 
 template <int R, bool STD, int RQ, bool FIX = false>
