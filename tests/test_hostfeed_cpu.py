@@ -72,3 +72,19 @@ def test_debug_break_stops_after_the_given_batch(feed):
     exe, d, ids, _ = feed
     lines, _ = run_cli(exe, d, "reads.blow5", "-K", "10", "--debug-break", "1")
     assert [ln.split("\t")[0] for ln in lines] == ids[:20]  # batches 0 and 1 (src/dtw_main.c:322-325)
+
+
+def test_threaded_epilogue_keeps_order_and_counters(feed, tmp_path):
+    """batches of >= 1024 reads: the per-read epilogue (PAF text, counters) runs on the -t worker threads in chunks of
+    512 reads; lines must still come out in input order, one per read, and the summary must add up"""
+    exe, d, ids, sigs = feed
+    n = 2600
+    big_ids = [f"big_{i:05d}" for i in range(n)]
+    big_sigs = [sigs[i % len(sigs)] for i in range(n)]
+    synth.write_blow5(str(d / "big.blow5"), big_ids, big_sigs)
+    for K in ("2600", "1100"):
+        lines, err = run_cli(exe, d, "big.blow5", "-K", K, "-B", "100G")
+        assert [ln.split("\t")[0] for ln in lines] == big_ids
+        assert [int(ln.split("\t")[1]) for ln in lines] == [len(s) for s in big_sigs]
+        m = re.search(r"total entries: (\d+)", err)
+        assert m and int(m.group(1)) == n
