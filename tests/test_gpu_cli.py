@@ -135,6 +135,33 @@ def test_cli_sam_is_byte_identical_to_reference(cli, tmp_path, case):
     assert out.count("@PG\tID:sigfish") == 1
 
 
+def test_cli_large_batches_use_the_threaded_epilogue(cli, tmp_path):
+    """batches of >= 1024 reads run the per-read epilogue (flip, offsets, MAPQ, PAF / SAM text) on the -t worker threads
+    in chunks of 512 reads: the output must be, byte for byte, what small batches (epilogue on the main thread) give,
+    for PAF and for SAM"""
+    k = 6
+    mean, stdv = synth.make_model(k)
+    seq = synth.random_sequence(12_000, np.random.default_rng(9))
+    base, _ = synth.simulate_reads([seq], k, mean, 150, seed=12, bases_per_read=430)
+    n = 2300
+    sigs = [base[i % len(base)] for i in range(n)]
+    ids = [f"read_{i:06d}" for i in range(n)]
+    fa, mf, b5 = str(tmp_path / "ref.fa"), str(tmp_path / "model.txt"), str(tmp_path / "reads.blow5")
+    synth.write_fasta(fa, ["chrT"], [seq])
+    synth.write_model_file(mf, k, mean, stdv)
+    synth.write_blow5(b5, ids, sigs)
+    for extra in ([], ["--sam"]):
+        outs = []
+        for K in ("4096", "200"):
+            r = subprocess.run([cli, "dtw", fa, b5, "--kmer-model", mf, "--gpus", "1", "-t", "8", "-K", K, "-B", "100G"] + extra,
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(r.stdout)
+        assert outs[0] == outs[1]
+        body = [ln for ln in outs[0].splitlines() if not ln.startswith("@")]
+        assert [ln.split("\t")[0] for ln in body] == ids
+
+
 def test_cli_c4_scale_matches_reference_binary(cli, tmp_path):
     """BASELINE.json configs[3] shape through both command lines on the same files: one 1 Mb contig (R10 k=9,
     both strands, 5e8 cells per read).  The unmodified reference binary (oracle/_ref/sigfish, ~0.3 s per read
