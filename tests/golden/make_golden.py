@@ -105,6 +105,11 @@ CASES = {
     "dna_sp1_from_end": ("sp1_dna", "nCoV-2019", 6, H.F_END, 250, 50),
     "dna_sp1_q100_p20": ("sp1_dna", "nCoV-2019", 6, 0, 100, 20),
     "dna_sp1_q300_p0": ("sp1_dna", "nCoV-2019", 6, 0, 300, 0),
+    # query sizes that run in the two-reads-per-warp layout with 10 / 13 / 15 rows per lane
+    "dna_synth48_q150": ("synth_dna48", "nCoV-2019", 6, 0, 150, 50),
+    "dna_sp1_q200_p20": ("sp1_dna", "nCoV-2019", 6, 0, 200, 20),
+    "dna_synth48_q230_from_end": ("synth_dna48", "nCoV-2019", 6, H.F_END, 230, 50),
+    "rna_sequin_q180": ("sequin_rna", "rnasequin", 5, H.F_RNA, 180, 50),
     "dna_synth48": ("synth_dna48", "nCoV-2019", 6, 0, 250, 50),
     "dna_synth48_from_end": ("synth_dna48", "nCoV-2019", 6, H.F_END, 250, 50),
     "dna_multi_contig": ("synth_dna_multi", "synth_multi", 6, 0, 250, 50),
@@ -167,7 +172,33 @@ SAM_CASES = ["dna_sp1_default", "dna_sp1_from_end", "dna_synth48", "dna_multi_co
              "rna_tail24_auto", "rna_synth32", "rna004_tx2000_invert", "rna004_tail16_auto"]
 
 
+def only_cases(names):
+    """adds the golden PAF of the named cases (fixtures must exist) without touching the other files"""
+    tmp = synth.tmpdir()
+    summary = json.load(open(os.path.join(HERE, "cases.json")))
+    for case in names:
+        reads, fasta, k, flags, q, p = CASES[case]
+        mean, stdv = synth.make_model(k)
+        synth.write_model_file(os.path.join(tmp, f"model_k{k}.txt"), k, mean, stdv)
+        ids, sg, sc = H.load_reads_npz(os.path.join(HERE, reads + ".npz"))
+        extra = CASE_EXTRA.get(case, {})
+        s5 = os.path.join(tmp, reads + ("_" + extra["kit"] if extra else "") + ".slow5")
+        synth.write_slow5_ascii(s5, ids, sg, rna=bool(flags & H.F_RNA), kit=extra.get("kit"), scalings=sc)
+        fa = os.path.join(tmp, fasta + ".fa")
+        with gzip.open(os.path.join(HERE, fasta + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        paf = H.run_ref(fa, s5, os.path.join(tmp, f"model_k{k}.txt"), flags=flags, q=q, p=p)
+        with open(os.path.join(HERE, "paf", case + ".paf"), "w") as f:
+            f.write(paf)
+        summary[case] = dict(reads=reads, fasta=fasta, k=k, flags=flags, q=q, p=p, rows=paf.count("\n"), **extra)
+        print(case, summary[case]["rows"], "rows")
+    with open(os.path.join(HERE, "cases.json"), "w") as f:
+        json.dump(summary, f, indent=1, sort_keys=True)
+
+
 def main():
+    if "--only" in sys.argv:
+        return only_cases(sys.argv[sys.argv.index("--only") + 1].split(","))
     os.makedirs(os.path.join(HERE, "paf"), exist_ok=True)
     tmp = synth.tmpdir()
 
