@@ -63,7 +63,7 @@ typedef struct {
     int32_t n_slots;      /* batches in flight (double buffering); 0 -> 2 */
     int32_t pore;         /* opt.pore_flag: 0 r9, 1 r10, 2 rna004 (only selects the jnn parameters) */
     int32_t reserved[5];  /* test knobs, keep 0: [0] checkpoint spacing, [1] restart window, [2] warm-up blocks of a piece,
-                             [3] 1 = no read pairing, 2 = pairing for every 128 < q <= 256,
+                             [3] 1 = no read pairing, 2 = --dtw-std pairs reads for every 128 < q <= 256 (default: 192 < q),
                              [4] piece length in checkpoint periods (< 0: never split) */
 } sfgpu_opt_t;
 
