@@ -533,7 +533,10 @@ int sf_s5_parse_head(const sf_s5file_t *f, const char *mem, size_t bytes, sf_rec
             memset(*scratch, 0, hdr);
         uint8_t *out = (uint8_t *)*scratch + hdr;
         size_t got = 0;
-        const int rc = sf_zlib_inflate((sf_inflater *)*scratch, (const uint8_t *)mem, bytes, out, SF_S5_HEAD_MAX, &got);
+        /* id length + id + read group, 4 doubles, signal length, the sample count of an svb-zd stream */
+        const int rc = sf_zlib_inflate_prefix((sf_inflater *)*scratch, (const uint8_t *)mem, bytes, out, SF_S5_HEAD_MAX, 4 + 32 + 8 + 4, &got)
+                           ? 1
+                           : sf_zlib_inflate((sf_inflater *)*scratch, (const uint8_t *)mem, bytes, out, SF_S5_HEAD_MAX, &got);
         if (rc < 0)
             return -1; /* the caller falls back to the full decoder (which lets zlib have the last word) */
         complete = rc == 0;

@@ -516,3 +516,222 @@ int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out
     *n_out = n;
     return 0;
 }
+
+/* ---- the beginning of a stream only -------------------------------------------------------------------------------
+ *
+ * sf_s5_parse_head() needs the first ~90 bytes of a record (id, scaling, sample count).  With the decoder above most
+ * of that call is spent filling lookup tables that are then asked ~100 times (gprof on tools/hostfeed: build_table
+ * 61 %).  For so few symbols a canonical code is decoded faster without tables: codes of one length are consecutive
+ * integers, and left-justified to 15 bits the codes grow with their length (RFC 1951 3.2.2), so the length of the next
+ * code is the first l with  window < limit[l]  (window = the next 15 bits, MSB first; limit[l] = one past the last
+ * code of length l, left-justified) and the symbol is sorted[offset[l] + (window >> (15 - l)) - first[l]].  Building
+ * limit / offset / sorted costs one pass over the code lengths.
+ *
+ * Handles the common layout only (first block dynamic, the requested bytes inside it); anything else -- and any
+ * damage -- returns 0 and the caller uses sf_zlib_inflate(), which has the last word on malformed streams. */
+typedef struct {
+    uint32_t limit[MAX_CODE_LEN + 2]; /* [l]: (first code of length l + count[l]) << (15 - l); [16] = sentinel */
+    uint16_t first[MAX_CODE_LEN + 1];
+    uint16_t offset[MAX_CODE_LEN + 1];
+    uint16_t sorted[N_LITLEN];
+    int min_len;
+} canon_code;
+
+/* 0, or -1 for an over-subscribed code or one without symbols */
+static int canon_build(canon_code *c, const uint8_t *lens, int n_sym)
+{
+    int count[MAX_CODE_LEN + 1] = {0};
+    for (int i = 0; i < n_sym; i++)
+        count[lens[i]]++;
+    count[0] = 0;
+    uint32_t code = 0;
+    int off = 0, space = 1;
+    c->min_len = 0;
+    for (int l = 1; l <= MAX_CODE_LEN; l++) {
+        code = (code + (uint32_t)count[l - 1]) << 1;
+        space = (space << 1) - count[l];
+        if (space < 0)
+            return -1;
+        c->first[l] = (uint16_t)code;
+        c->offset[l] = (uint16_t)off;
+        c->limit[l] = (code + (uint32_t)count[l]) << (MAX_CODE_LEN - l);
+        off += count[l];
+        if (count[l] && !c->min_len)
+            c->min_len = l;
+    }
+    c->limit[MAX_CODE_LEN + 1] = 0xffffffffu;
+    if (!c->min_len)
+        return -1;
+    uint16_t next[MAX_CODE_LEN + 1];
+    memcpy(next, c->offset, sizeof next);
+    for (int i = 0; i < n_sym; i++)
+        if (lens[i])
+            c->sorted[next[lens[i]]++] = (uint16_t)i;
+    return 0;
+}
+
+static const uint8_t k_rev8[256] = {
+#define R2(n) (n), (n) + 2 * 64, (n) + 1 * 64, (n) + 3 * 64
+#define R4(n) R2(n), R2((n) + 2 * 16), R2((n) + 1 * 16), R2((n) + 3 * 16)
+#define R6(n) R4(n), R4((n) + 2 * 4), R4((n) + 1 * 4), R4((n) + 3 * 4)
+    R6(0), R6(2), R6(1), R6(3)
+#undef R2
+#undef R4
+#undef R6
+};
+
+/* the symbol of the next code in the low bits of bb (>= 15 valid or zero-padded bits); *len = its length, 0 if the
+ * bits are no code (incomplete code) */
+static inline int canon_decode(const canon_code *c, uint64_t bb, int *len)
+{
+    const uint32_t w = (((uint32_t)k_rev8[bb & 255] << 8) | k_rev8[(bb >> 8) & 255]) >> 1; /* 15 bits, MSB first */
+    int l = c->min_len;
+    while (w >= c->limit[l])
+        l++;
+    if (l > MAX_CODE_LEN) {
+        *len = 0;
+        return 0;
+    }
+    *len = l;
+    return c->sorted[c->offset[l] + (w >> (MAX_CODE_LEN - l)) - c->first[l]];
+}
+
+/* Decodes the first min(cap_out, 2 + u16le(out[0..2)) + tail) bytes of the zlib stream in[0 .. n_in): a u16 length,
+ * that many bytes, and `tail` more (the layout of a BLOW5 record: id length, id, fixed fields).  Returns 1 with
+ * *n_out = that many bytes, or 0 = not decoded here. */
+int sf_zlib_inflate_prefix(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap_out, size_t tail, size_t *n_out)
+{
+    if (n_in < 6 || cap_out < 2)
+        return 0;
+    if ((in[0] & 15) != 8 || (in[0] >> 4) > 7 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20))
+        return 0;
+    if (!d->ready) {
+        for (int i = 0; i < N_LITLEN; i++) d->sym_litlen[i] = litlen_symbol(i);
+        for (int i = 0; i < N_DIST; i++) d->sym_dist[i] = dist_symbol(i);
+        for (int i = 0; i < N_PRECODE; i++) d->sym_precode[i] = precode_symbol(i);
+        d->ready = 1;
+    }
+    const uint8_t *ip = in + 2;
+    const uint8_t *const in_end = in + n_in;
+    uint64_t bb = 0;
+    unsigned bc = 0;
+    /* the same reader as above, except that running out of input is "not decoded here" */
+#define PREFILL()                                                 \
+    do {                                                          \
+        if (in_end - ip >= 8) {                                   \
+            bb |= load64le(ip) << bc;                             \
+            ip += (63 - bc) >> 3;                                 \
+            bc |= 56;                                             \
+        } else {                                                  \
+            while (bc <= 56 && ip < in_end) {                     \
+                bb |= (uint64_t)*ip++ << bc;                      \
+                bc += 8;                                          \
+            }                                                     \
+        }                                                         \
+    } while (0)
+#define PDROP(n)                                                  \
+    do {                                                          \
+        if ((unsigned)(n) > bc)                                   \
+            return 0;                                             \
+        bb >>= (n);                                               \
+        bc -= (unsigned)(n);                                      \
+    } while (0)
+    PREFILL();
+    if (((bb >> 1) & 3) != 2)
+        return 0; /* stored / fixed first block: rare (tiny or uncompressible records) */
+    PDROP(3);
+    const int hlit = (int)BITS(5) + 257;
+    const int hdist = (int)((bb >> 5) & 31) + 1;
+    const int hclen = (int)((bb >> 10) & 15) + 4;
+    PDROP(14);
+    if (hlit > 286 || hdist > 30)
+        return 0;
+    uint8_t plen[N_PRECODE] = {0};
+    for (int i = 0; i < hclen; i++) {
+        PREFILL();
+        plen[k_precode_order[i]] = (uint8_t)BITS(3);
+        PDROP(3);
+    }
+    if (build_table(plen, N_PRECODE, 7, d->sym_precode, d->precode, 0))
+        return 0;
+    uint8_t lens[N_LITLEN + N_DIST];
+    int n = 0;
+    while (n < hlit + hdist) {
+        PREFILL();
+        const uint32_t e = d->precode[BITS(7)];
+        if (E_TYPE(e) != T_LITERAL)
+            return 0;
+        PDROP(E_NBITS(e));
+        const int sym = (int)E_VALUE(e);
+        if (sym < 16) {
+            lens[n++] = (uint8_t)sym;
+            continue;
+        }
+        int rep;
+        uint8_t v = 0;
+        if (sym == 16) {
+            if (n == 0)
+                return 0;
+            v = lens[n - 1];
+            rep = 3 + (int)BITS(2);
+            PDROP(2);
+        } else if (sym == 17) {
+            rep = 3 + (int)BITS(3);
+            PDROP(3);
+        } else {
+            rep = 11 + (int)BITS(7);
+            PDROP(7);
+        }
+        if (n + rep > hlit + hdist)
+            return 0;
+        memset(lens + n, v, (size_t)rep);
+        n += rep;
+    }
+    if (lens[256] == 0)
+        return 0;
+    canon_code lc, dc;
+    if (canon_build(&lc, lens, hlit))
+        return 0;
+    const int have_dist = canon_build(&dc, lens + hlit, hdist) == 0;
+
+    size_t want = cap_out, got = 0;
+    while (got < want) {
+        PREFILL();
+        int l;
+        const int sym = canon_decode(&lc, bb, &l);
+        if (!l)
+            return 0;
+        PDROP(l);
+        if (sym < 256) {
+            out[got++] = (uint8_t)sym;
+        } else {
+            if (sym == 256 || sym > 285 || !have_dist)
+                return 0; /* the block ends inside the prefix: the general decoder deals with it */
+            const uint32_t x = k_len_extra[sym - 257];
+            const uint32_t len = k_len_base[sym - 257] + BITS(x);
+            PDROP(x);
+            const int ds = canon_decode(&dc, bb, &l);
+            if (!l || ds > 29)
+                return 0;
+            PDROP(l);
+            const uint32_t y = k_dist_extra[ds];
+            const uint32_t dist = k_dist_base[ds] + BITS(y);
+            PDROP(y);
+            if (dist > got)
+                return 0;
+            for (uint32_t i = 0; i < len && got < want; i++, got++)
+                out[got] = out[got - dist];
+        }
+        if (want == cap_out && got >= 2) {
+            const size_t w = 2 + ((size_t)out[0] | ((size_t)out[1] << 8)) + tail;
+            if (w < want)
+                want = w;
+            if (got > want)
+                got = want;
+        }
+    }
+#undef PREFILL
+#undef PDROP
+    *n_out = got;
+    return 1;
+}

@@ -30,6 +30,11 @@ typedef struct {
  * -1 = corrupt or unsupported stream. */
 int sf_zlib_inflate(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap_out, size_t *n_out);
 
+/* The beginning of a stream whose plain text starts with a u16 length: decodes min(cap_out, 2 + that length + tail)
+ * bytes without building lookup tables (the head of a BLOW5 record: id length, id, fixed fields).  1 = done, *n_out
+ * bytes are valid; 0 = not decoded here (uncommon layout or damage): use sf_zlib_inflate(). */
+int sf_zlib_inflate_prefix(sf_inflater *d, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap_out, size_t tail, size_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

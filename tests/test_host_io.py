@@ -227,6 +227,69 @@ def test_inflate_matches_zlib_on_all_block_types(host, seed):
             assert got == zlib.decompress(bytes(bad))
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_inflate_prefix_agrees_with_the_full_decoder(host, seed):
+    """sf_zlib_inflate_prefix (table-free canonical decoder behind sf_s5_parse_head): whenever it answers, its bytes
+    are the beginning of what zlib gives and their number is min(cap, 2 + u16 + tail); it declines stored / fixed
+    first blocks and prefixes that do not lie inside the first block; damaged streams never make it overrun, and
+    whatever it returns for them is what the full decoder returns for the same bytes"""
+    import struct
+    import zlib
+    host.sf_zlib_inflate_prefix.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                            C.POINTER(C.c_size_t)]
+    host.sf_zlib_inflate_prefix.restype = C.c_int
+    state = C.create_string_buffer(1 << 16)
+    full = _inflater(host)
+    rng = np.random.default_rng(100 + seed)
+
+    def prefix(data, cap, tail):
+        out = C.create_string_buffer(cap + 64)
+        out.raw = b"\xa5" * (cap + 64)
+        n = C.c_size_t(0)
+        rc = host.sf_zlib_inflate_prefix(state, data, len(data), out, cap, tail, C.byref(n))
+        assert out.raw[cap:] == b"\xa5" * 64  # never writes past cap
+        return rc, out.raw[:n.value]
+
+    answered = declined = 0
+    for it in range(400):
+        idl = int(rng.choice([0, 1, 8, 36, 36, 36, 255, 300, 5000]))
+        rid = bytes(rng.integers(48, 123, idl, dtype=np.uint8)) if rng.random() < .8 else b"a" * idl  # runs: matches
+        n = int(rng.choice([0, 1, 3, 50, 600, 9000, 40000]))
+        raw = struct.pack("<H", idl) + rid + struct.pack("<I4dQ", 0, 8192.0, float(rng.integers(-300, 300)), 1437.98, 4000.0, n) + \
+            _payload(rng, int(rng.integers(0, 6)), n)
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY,
+                                zlib.Z_RLE, zlib.Z_FIXED]))
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, int(rng.integers(9, 16)), 8, strat)
+        cut = int(rng.integers(0, len(raw) + 1)) if rng.random() < .2 else len(raw)
+        comp = co.compress(raw[:cut]) + (co.flush(zlib.Z_FULL_FLUSH) if cut < len(raw) else b"") + co.compress(raw[cut:]) + co.flush()
+        cap = int(rng.choice([2, 3, 60, 384, 384, 384, 1000]))
+        tail = int(rng.choice([0, 48, 48, 48, 100]))
+        rc, got = prefix(comp, cap, tail)
+        assert rc in (0, 1)
+        if rc == 1:
+            answered += 1
+            assert len(got) == min(cap, 2 + idl + tail) and got == raw[:len(got)], (seed, it)
+        else:
+            declined += 1
+        # damage: flipped bits, truncation
+        bad = bytearray(comp)
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        if rng.random() < .4:
+            bad = bad[:int(rng.integers(0, len(bad) + 1))]
+        rc, got = prefix(bytes(bad), cap, tail)
+        if rc == 1:
+            # the same bytes the table decoder produces when it is stopped at that many output bytes
+            out = C.create_string_buffer(len(got) + 1)
+            m = C.c_size_t(0)
+            rc2 = host.sf_zlib_inflate(C.create_string_buffer(1 << 16), bytes(bad), len(bad), out, len(got), C.byref(m))
+            if rc2 == 1:
+                assert out.raw[:m.value] == got[:m.value], (seed, it)
+            elif rc2 == 0:
+                assert out.raw[:m.value] == got
+    assert answered > 100 and declined > 20, (answered, declined)
+
+
 def test_blow5_records_decode_identically_with_every_codec_combination(host, tmp_path):
     """zlib on / off x svb-zd on / off, signals with the extreme deltas (4-byte svb codes) and lengths that
     are not a multiple of four (the tail of the fast svb loop)"""
