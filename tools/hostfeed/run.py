@@ -77,9 +77,28 @@ def main():
     seq = synth.random_sequence(1_000_000, np.random.default_rng(1))
     blow5 = os.path.join(d, f"reads_{args.reads}.blow5")
     if not os.path.exists(blow5):
-        base, _ = synth.simulate_reads([seq], k, mean, min(args.reads, 4000), seed=4242, bases_per_read=450)
-        sigs = [base[i % len(base)] for i in range(args.reads)]
-        synth.write_blow5(blow5, [f"read_{i:07d}" for i in range(args.reads)], sigs, kit="sqk-lsk114")
+        # a unit of at most 4000 distinct reads, its records repeated (compressing every record from Python costs
+        # 0.2 ms per read: 300 k reads took over a minute, which once cost a whole gpurun call its time limit)
+        unit = min(args.reads, 4000)
+        base, _ = synth.simulate_reads([seq], k, mean, unit, seed=4242, bases_per_read=450)
+        one = blow5 + ".unit"
+        synth.write_blow5(one, [f"read_{i:07d}" for i in range(unit)], base, kit="sqk-lsk114")
+        raw = open(one, "rb").read()
+        os.remove(one)
+        hlen = 64 + 4 + int.from_bytes(raw[64:68], "little")
+        reps, rest = divmod(args.reads, unit)
+        body = raw[hlen:-5]
+        tmp = blow5 + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(raw[:hlen])
+            for _ in range(reps):
+                f.write(body)
+            o = 0
+            for _ in range(rest):  # whole records: u64 size + bytes
+                o += 8 + int.from_bytes(body[o:o + 8], "little")
+            f.write(body[:o])
+            f.write(b"5WOLB")
+        os.replace(tmp, blow5)  # never leave a truncated file behind
     synth.write_model_file(os.path.join(d, "model.txt"), k, mean, stdv)
     synth.write_fasta(os.path.join(d, "ref.fa"), ["chrS"], [seq])
     cmd = [exe, "dtw", os.path.join(d, "ref.fa"), blow5, "--kmer-model", os.path.join(d, "model.txt"), "-t", str(args.t),
