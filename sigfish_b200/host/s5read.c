@@ -486,6 +486,8 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
         return -1;
     free(r->read_id);
     r->read_id = (char *)malloc((size_t)idl + 1);
+    if (!r->read_id)
+        return -1;
     memcpy(r->read_id, p + o, idl);
     r->read_id[idl] = 0;
     o += idl;
@@ -501,7 +503,8 @@ static int parse_binary(const sf_s5file_t *f, const char *mem, size_t bytes, sf_
             return -1;
         if (rec_reserve_signal(r, (size_t)len))
             return -1;
-        memcpy(r->raw_signal, p + o, (size_t)len * 2);
+        if (len) /* an empty read may have no buffer at all */
+            memcpy(r->raw_signal, p + o, (size_t)len * 2);
         r->len_raw_signal = len;
     } else {
         if (len > n - o)
@@ -552,6 +555,8 @@ int sf_s5_parse_head(const sf_s5file_t *f, const char *mem, size_t bytes, sf_rec
         return -1;
     free(r->read_id);
     r->read_id = (char *)malloc((size_t)idl + 1);
+    if (!r->read_id)
+        return -1;
     memcpy(r->read_id, p + o, idl);
     r->read_id[idl] = 0;
     o += idl;
