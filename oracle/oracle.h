@@ -126,6 +126,10 @@ void orc_align_means(const orc_ref_t *ref, const float *means, int32_t n, uint32
 void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation,
                   float offset, float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit);
 
+/* the same, also returning the (window-normalised) event table; *ev_out is freed with orc_free */
+void orc_map_read_events(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation, float offset,
+                         float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit, orc_event_t **ev_out);
+
 /* paf_str (sigfish.c:628-660) -- returns the number of bytes written (excl. NUL) */
 int orc_paf_line(char *buf, size_t cap, const orc_hit_t *hit, const char *read_id,
                  const char *rname, int32_t ref_seq_len, int64_t len_raw_signal);

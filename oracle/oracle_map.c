@@ -205,6 +205,14 @@ void orc_map_read(const orc_ref_t *ref, const int16_t *raw, int64_t n, float dig
     map_read_core(ref, raw, n, digitisation, offset, range, flags, q, p, hit, NULL);
 }
 
+/* orc_map_read that also hands out the event table it worked on (normalised in place by the window step; caller
+ * frees with orc_free): what a test double of the device needs to rebuild the winner's warping path */
+void orc_map_read_events(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation, float offset,
+                         float range, uint32_t flags, int32_t q, int32_t p, orc_hit_t *hit, orc_event_t **ev_out)
+{
+    map_read_core(ref, raw, n, digitisation, offset, range, flags, q, p, hit, ev_out);
+}
+
 int orc_map_read_sam(const orc_ref_t *ref, const int16_t *raw, int64_t n, float digitisation, float offset,
                      float range, uint32_t flags, int32_t q, int32_t p, const char *read_id,
                      const char *const *rnames, char *buf, size_t cap)

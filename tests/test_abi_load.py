@@ -51,3 +51,26 @@ def test_argument_validation_happens_before_device_use(lib):
     opt.prefix_size = -1
     assert lib.sfgpu_create(C.byref(h), C.byref(opt), lm.ctypes.data_as(C.c_void_p)) == -2
     assert b"prefix_size" in lib.sfgpu_strerror(None)
+
+
+def test_product_never_touches_the_oracle_or_the_test_double():
+    """oracle/ and tests/mockdev/ are test infrastructure: no product source may include, link, load or name them, and
+    the built product libraries must not depend on them"""
+    import glob
+    import re
+    import subprocess
+    ROOT = H.ROOT
+    pat = re.compile(r"oracle[/_.]|liboracle|mockdev|sfgpu_oracle|sfgpu_null", re.I)
+    srcs = [f for ext in ("c", "h", "cu", "cuh", "py") for f in glob.glob(os.path.join(ROOT, "sigfish_b200", "**", "*." + ext), recursive=True)]
+    srcs += glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.join(ROOT, "Makefile")]
+    assert len(srcs) > 20
+    for f in srcs:
+        for n, line in enumerate(open(f, errors="replace"), 1):
+            if f.endswith("Makefile") and line.lstrip().startswith(("#", "oracle:", ".PHONY", "test:", "\t$(MAKE) -C oracle")):
+                continue  # the convenience targets that build / run the test infrastructure
+            assert not pat.search(line), f"{f}:{n}: {line.strip()}"
+    for so in ("libsfgpu.so", "libsfhost.so", "sigfish-b200"):
+        p = os.path.join(ROOT, "sigfish_b200", so)
+        if os.path.exists(p):
+            needed = subprocess.run(["readelf", "-d", p], capture_output=True, text=True).stdout
+            assert "oracle" not in needed and "mockdev" not in needed, so

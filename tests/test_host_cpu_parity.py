@@ -1,0 +1,216 @@
+"""The product's HOST code end to end on the CPU: sigfish_b200/host/*.c (readers, batch loop, read sharding over
+contexts, device-decode fallback, threaded epilogue, PAF / SAM writers) linked against a TEST DOUBLE of libsfgpu.so
+that answers include/sfgpu.h with the CPU oracle (tests/mockdev/sfgpu_oracle.c).  Its output must be, byte for byte,
+what the unmodified reference binary printed (tests/golden/paf, tests/golden/sam) -- the same comparison
+tests/test_gpu_cli.py makes with the CUDA library, minus the kernels.  Nothing here is part of the product: the double
+is built into tests/mockdev/_build/ and only this file runs it."""
+import glob
+import gzip
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from sigfish_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MOCK = os.path.join(HERE, "mockdev")
+BUILD = os.path.join(MOCK, "_build")
+CASES = json.load(open(os.path.join(H.GOLDEN, "cases.json")))
+SAM_CASES = sorted(f[:-4] for f in os.listdir(os.path.join(H.GOLDEN, "sam")))
+# cases the CPU oracle needs long for (2000 transcripts; 4.4 M reference columns per read with --full-ref): one of them
+# runs here, the GPU suite runs them all
+SLOW = {"rna004_tx2000_invert_full_ref", "rna004_tx2000_default", "rna004_tx2000_dtw_std"}
+SLOW_SAM = SLOW | {"rna004_tx2000_invert", "rna004_tail16_auto"}
+
+
+@pytest.fixture(scope="module")
+def cli():
+    H.build_oracle()
+    os.makedirs(BUILD, exist_ok=True)
+    inc = os.path.join(H.ROOT, "include")
+    host = os.path.join(H.ROOT, "sigfish_b200", "host")
+    lib = os.path.join(BUILD, "libsfgpu.so")
+    exe = os.path.join(BUILD, "sigfish-b200-oracle-device")
+    srcs = sorted(glob.glob(os.path.join(host, "*.c")))
+    deps = srcs + glob.glob(os.path.join(host, "*.h")) + [os.path.join(MOCK, "sfgpu_oracle.c"), H.ORACLE_SO,
+                                                           os.path.join(inc, "sfgpu.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["gcc", "-O2", "-g", "-std=c99", "-Wall", "-fPIC", "-shared", "-I", inc, "-I", H.ORACLE_DIR, "-o", lib,
+                        os.path.join(MOCK, "sfgpu_oracle.c"), "-L", H.ORACLE_DIR, "-loracle", "-Wl,-rpath," + H.ORACLE_DIR,
+                        "-lz", "-lm"], check=True)
+        subprocess.run(["gcc", "-O2", "-g", "-std=c99", "-Wall", "-D_GNU_SOURCE", "-I", inc, "-o", exe] + srcs +
+                       ["-L", BUILD, "-lsfgpu", "-Wl,-rpath," + BUILD, "-Wl,-rpath," + H.ORACLE_DIR, "-lz", "-lpthread", "-lm"],
+                       check=True)
+    return exe
+
+
+def _inputs(tmp, case, fmt):
+    c = CASES[case]
+    fa = os.path.join(tmp, "ref.fa")
+    if c["fasta"] in H.GENERATED_FASTA:
+        H.write_case_fasta(c, fa)
+    else:
+        with gzip.open(os.path.join(H.GOLDEN, c["fasta"] + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    ids, sigs, sc = H.case_reads(c)
+    rna = bool(c["flags"] & H.F_RNA)
+    reads = os.path.join(tmp, "reads." + fmt)
+    if fmt == "slow5":
+        synth.write_slow5_ascii(reads, ids, sigs, rna=rna, kit=H.case_kit(c), scalings=sc)
+    else:
+        synth.write_blow5(reads, ids, sigs, rna=rna, kit=H.case_kit(c), scalings=sc)
+    mean, stdv = synth.make_model(c["k"])
+    mf = os.path.join(tmp, "model.txt")
+    synth.write_model_file(mf, c["k"], mean, stdv)
+    return c, fa, reads, mf
+
+
+def _run(cli, c, fa, reads, mf, extra=(), gpus=1, env=None):
+    cmd = [cli, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"]), "--gpus", str(gpus)] + \
+        H.flags_to_cli(c["flags"]) + list(extra)
+    e = dict(os.environ, MOCK_GPUS=str(gpus))
+    e.update(env or {})
+    r = subprocess.run(cmd, capture_output=True, text=True, env=e)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout, r.stderr
+
+
+def _strip_pg(t):
+    return "".join(l for l in t.splitlines(keepends=True) if not l.startswith("@PG"))
+
+
+@pytest.mark.parametrize("case", sorted(set(CASES) - SLOW))
+def test_host_paf_is_byte_identical_to_reference(cli, tmp_path, case):
+    fmt = "slow5" if sum(map(ord, case)) % 2 else "blow5"  # the other format than tests/test_gpu_cli.py uses for the case
+    c, fa, reads, mf = _inputs(str(tmp_path), case, fmt)
+    out, err = _run(cli, c, fa, reads, mf)
+    assert out == open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read()
+    assert "total entries" in err
+
+
+@pytest.mark.parametrize("case", [c for c in SAM_CASES if c not in SLOW_SAM])
+def test_host_sam_is_byte_identical_to_reference(cli, tmp_path, case):
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, _ = _run(cli, c, fa, reads, mf, ["--sam", "-K", "5"])
+    assert _strip_pg(out) == _strip_pg(open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read())
+    assert out.count("@PG\tID:sigfish") == 1
+
+
+@pytest.mark.parametrize("case,extra,gpus,env", [
+    ("dna_synth48", ["-K", "7", "-t", "3"], 1, {}),
+    ("dna_synth48", ["-B", "30K"], 1, {}),
+    ("dna_multi_contig", ["-K", "1"], 1, {}),
+    ("dna_synth48", ["-K", "20"], 3, {}),                           # reads sharded over three contexts
+    ("dna_synth48", [], 8, {}),
+    ("rna_synth32", ["-K", "9", "-t", "4"], 2, {}),
+    ("dna_synth48", ["--device-decode=no"], 2, {}),                 # records decoded by the host reader
+    ("dna_synth48", ["-K", "11"], 2, {"MOCK_REJECT_RECORDS": "1"}),  # the device rejects the records: host fallback
+    ("rna_tail24_auto", ["-K", "5"], 2, {"MOCK_REJECT_RECORDS": "1"}),
+])
+def test_host_batching_sharding_and_decode_paths_do_not_change_output(cli, tmp_path, case, extra, gpus, env):
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    out, err = _run(cli, c, fa, reads, mf, extra, gpus=gpus, env=env)
+    assert out == open(os.path.join(H.GOLDEN, "paf", case + ".paf")).read()
+    assert f"on {gpus} GPU(s)" in err
+    if env:
+        assert "decoding this batch on the host" in err
+
+
+def test_host_sharded_sam_and_debug_break(cli, tmp_path):
+    for case in ("rna_tail24_auto", "dna_synth48"):
+        c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+        out, _ = _run(cli, c, fa, reads, mf, ["--sam", "-K", "9"], gpus=2)
+        assert _strip_pg(out) == _strip_pg(open(os.path.join(H.GOLDEN, "sam", case + ".sam")).read()), case
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_synth48", "blow5")
+    out, _ = _run(cli, c, fa, reads, mf, ["--debug-break", "1", "-K", "10"])  # stops after N + 1 batches (dtw_main.c:322-325)
+    want = open(os.path.join(H.GOLDEN, "paf", "dna_synth48.paf")).read()
+    assert out == "".join(want.splitlines(keepends=True)[:20])
+
+
+def test_host_threaded_epilogue_on_large_batches(cli, tmp_path):
+    """batches of >= 1024 reads run the epilogue on the -t threads in chunks of 512 reads: same bytes as small batches"""
+    k = 6
+    mean, stdv = synth.make_model(k)
+    seq = synth.random_sequence(1500, np.random.default_rng(9))
+    base, _ = synth.simulate_reads([seq], k, mean, 40, seed=12, bases_per_read=300)
+    n = 2300
+    sigs = [base[i % len(base)] for i in range(n)]
+    ids = [f"read_{i:06d}" for i in range(n)]
+    fa, mf, b5 = str(tmp_path / "ref.fa"), str(tmp_path / "model.txt"), str(tmp_path / "reads.blow5")
+    synth.write_fasta(fa, ["chrT"], [seq])
+    synth.write_model_file(mf, k, mean, stdv)
+    synth.write_blow5(b5, ids, sigs)
+    c = dict(q=100, p=50, flags=0)
+    for extra in ([], ["--sam"]):
+        a, _ = _run(cli, c, fa, b5, mf, ["-t", "8", "-K", "4096", "-B", "100G"] + extra, gpus=2)
+        b, _ = _run(cli, c, fa, b5, mf, ["-t", "2", "-K", "200", "-B", "100G"] + extra)
+        assert a == b
+        assert [ln.split("\t")[0] for ln in a.splitlines() if not ln.startswith("@")] == ids
+
+
+def _fuzz_seeds():
+    """12 seeds in the suite; SF_FUZZ_SEEDS=first:last runs another range (long runs are recorded in DESIGN.md 3)"""
+    r = os.environ.get("SF_FUZZ_SEEDS", "")
+    if ":" in r:
+        a, b = r.split(":")
+        return range(int(a), int(b))
+    return range(12)
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("seed", _fuzz_seeds())
+def test_host_fuzz_matches_reference_binary(cli, tmp_path, seed):
+    """seeded fuzz of the command line over the oracle device against the unmodified reference binary run right now
+    (build container only): chemistry, flags, q, p (incl. -1), contigs, reads, batch size, contexts; PAF and SAM"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(9000 + seed)
+    rna = bool(rng.integers(0, 2))
+    k = (9 if seed % 3 == 2 else 5) if rna else int(rng.choice([6, 9]))
+    rna004 = rna and k == 9
+    flags = 0
+    p = int(rng.choice([0, 10, 50, 50, 120]))
+    if rna:
+        flags = H.F_RNA | int(rng.choice([0, H.F_DTW, H.F_INV, H.F_REF, H.F_DTW | H.F_REF, H.F_INV | H.F_REF]))
+        if rng.integers(0, 3) == 0 and not (flags & H.F_INV):
+            p = -1
+    if p >= 0 and rng.integers(0, 3) == 0:
+        flags |= H.F_END
+    q = int(rng.choice([25, 60, 97, 130, 250, 250, 333]))
+    mean, stdv = synth.make_model(k, seed=51 + seed)
+    seqs = [synth.random_sequence(int(n), rng) for n in rng.integers(700, 4000, size=int(rng.integers(1, 5)))]
+    names = [f"c{i}" for i in range(len(seqs))]
+    sigs, scs = [], []
+    for r in range(9):
+        if rna and p < 0 and r % 2 == 0:
+            s, _ = synth.simulate_rna_reads_with_tail(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), bases_per_read=500)
+        else:
+            s, _ = synth.simulate_reads(seqs, k, mean, 1, seed=int(rng.integers(1 << 30)), rna=rna,
+                                        bases_per_read=int(rng.choice([150, 300, 450, 700])), min_samples=700)
+        sigs.append(s[0])
+        scs.append(synth.RNA_SCALING if rna else synth.DNA_SCALING)
+    ids = [f"r{i}" for i in range(len(sigs))]
+    fa, mf = str(tmp_path / "ref.fa"), str(tmp_path / "model.txt")
+    fmt = "slow5" if seed % 4 == 3 else "blow5"
+    s5 = str(tmp_path / ("reads." + fmt))
+    synth.write_fasta(fa, names, seqs)
+    kit = "sqk-rna004" if rna004 else ("sqk-lsk114" if k == 9 else None)
+    if fmt == "slow5":
+        synth.write_slow5_ascii(s5, ids, sigs, rna=rna, kit=kit, scalings=scs)
+    else:
+        synth.write_blow5(s5, ids, sigs, rna=rna, kit=kit, scalings=scs, record_zlib=bool(seed % 2), signal_svb=bool(seed % 3))
+    synth.write_model_file(mf, k, mean, stdv)
+    c = dict(q=q, p=p, flags=flags)
+    gpus = int(rng.integers(1, 4))
+    extra = ["-K", str(int(rng.integers(1, 6))), "-t", str(int(rng.integers(1, 5)))]
+    out, err = _run(cli, c, fa, s5, mf, extra, gpus=gpus)
+    assert out == H.run_ref(fa, s5, mf, flags=flags, q=q, p=p), (flags, q, p, gpus, extra)
+    if not flags & H.F_DTW:  # the reference aborts on --dtw-std --sam (sigfish.c:669)
+        out, _ = _run(cli, c, fa, s5, mf, extra + ["--sam"], gpus=gpus)
+        want = H.run_ref(fa, s5, mf, flags=flags, q=q, p=p, extra=["--sam"])
+        assert _strip_pg(out) == _strip_pg(want), (flags, q, p, gpus, extra)
