@@ -214,3 +214,32 @@ def test_host_fuzz_matches_reference_binary(cli, tmp_path, seed):
         out, _ = _run(cli, c, fa, s5, mf, extra + ["--sam"], gpus=gpus)
         want = H.run_ref(fa, s5, mf, flags=flags, q=q, p=p, extra=["--sam"])
         assert _strip_pg(out) == _strip_pg(want), (flags, q, p, gpus, extra)
+
+
+# ---------------------------------------------------------------- the reference's own host code over the test double
+
+REF_ACC_BIN = os.path.join(H.ORACLE_DIR, "_ref", "sigfish_acc")
+ACC_CASES = ["dna_sp1_default", "rna_sequin_default", "dna_synth48", "dna_sp1_from_end", "dna_short_reads", "dna_r10_k9",
+             "rna_sequin_invert", "rna_sequin_dtw_std", "rna_sequin_q500_auto", "rna_tail24_auto"]
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("case", ACC_CASES)
+def test_patched_reference_over_the_test_double_matches_golden(cli, tmp_path, case):
+    """integration/sigfish_acc.patch (the reference built with its accelerator hooks bound to sfgpu.h,
+    oracle/_ref/sigfish_acc) with the test double in place of libsfgpu.so: the glue of the patch (acc_b200.h: submit,
+    collect, the fields it writes back into db, paf_str / sam_str on them) reproduces the golden PAF / SAM on the CPU.
+    The GPU suite runs the same binary over the CUDA library."""
+    if not os.path.exists(REF_ACC_BIN):
+        pytest.skip("oracle/_ref/sigfish_acc not built (needs /root/reference at build time)")
+    c, fa, reads, mf = _inputs(str(tmp_path), case, "blow5")
+    env = dict(os.environ, LD_LIBRARY_PATH=BUILD)  # the binary finds libsfgpu.so through a RUNPATH: this comes first
+    for sam in (False, True):
+        if sam and (case not in SAM_CASES or c["flags"] & H.F_DTW):
+            continue
+        cmd = [REF_ACC_BIN, "dtw", fa, reads, "--kmer-model", mf, "-q", str(c["q"]), "-p", str(c["p"]), "-t", "4"] + \
+            H.flags_to_cli(c["flags"]) + (["--sam"] if sam else [])
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        want = open(os.path.join(H.GOLDEN, "sam" if sam else "paf", case + (".sam" if sam else ".paf"))).read()
+        assert _strip_pg(r.stdout) == _strip_pg(want), (case, sam)  # (without the double there is no device: exit 1)
