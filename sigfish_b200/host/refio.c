@@ -1,8 +1,7 @@
 /* refio.c -- FASTA and k-mer model file readers of the host pipeline.
  *
- * FASTA: what gen_ref() gets from kseq (reference src/genref.c:100-127): the name is the header up
- * to the first white space, the sequence is every following line with white space removed; plain or
- * gzip files.
+ * FASTA / FASTQ: what gen_ref() gets from kseq (reference src/genref.c:100-127, src/kseq.h:184-224): the name is
+ * the header up to the first white space, the sequence is every following line; plain or gzip files.
  * Model: the text format read_model() accepts (reference src/model.c:38-131): optional "#k\t<K>"
  * line, optional header line, then 4^K rows "kmer\tlevel_mean\tlevel_stdv..." taken in file order
  * (the k-mer text is not looked up).
@@ -16,69 +15,166 @@
 
 #define MAX_KMER_SIZE 9
 
+/* buffered characters of a (possibly gzip-compressed) file */
+typedef struct {
+    gzFile fp;
+    unsigned char *buf;
+    int n, pos, eof;
+} chars_t;
+#define CHARS_BUF (1 << 20)
+
+static int chars_fill(chars_t *r)
+{
+    if (r->eof)
+        return -1;
+    r->n = gzread(r->fp, r->buf, CHARS_BUF);
+    r->pos = 0;
+    if (r->n <= 0) {
+        r->n = 0;
+        r->eof = 1;
+        return -1;
+    }
+    return 0;
+}
+static inline int chars_get(chars_t *r)
+{
+    if (r->pos >= r->n && chars_fill(r))
+        return -1;
+    return r->buf[r->pos++];
+}
+static inline int chars_at_end(chars_t *r) { return r->pos >= r->n && chars_fill(r); }
+
+typedef struct {
+    char *s;
+    size_t n, cap;
+} text_t;
+
+static void text_put(text_t *t, const unsigned char *p, size_t n)
+{
+    if (t->n + n + 1 > t->cap) {
+        while (t->n + n + 1 > t->cap)
+            t->cap = t->cap ? t->cap * 2 : 1 << 16;
+        t->s = (char *)realloc(t->s, t->cap);
+    }
+    memcpy(t->s + t->n, p, n);
+    t->n += n;
+}
+
+/* appends the rest of the current line (without its line feed) to t, or skips it when t is NULL; a carriage return
+ * that ends what t then holds past `from` is dropped, as long as more than one character stands there (kseq's rule for
+ * Windows line ends: it looks at the whole string it is appending to) */
+static void chars_line(chars_t *r, text_t *t, size_t from)
+{
+    if (chars_at_end(r))
+        return; /* nothing follows: kseq leaves the string as it is */
+    for (;;) {
+        if (r->pos >= r->n && chars_fill(r))
+            break;
+        const unsigned char *b = r->buf + r->pos;
+        const unsigned char *nl = (const unsigned char *)memchr(b, '\n', (size_t)(r->n - r->pos));
+        const size_t len = nl ? (size_t)(nl - b) : (size_t)(r->n - r->pos);
+        if (t)
+            text_put(t, b, len);
+        r->pos += (int)len + (nl ? 1 : 0);
+        if (nl)
+            break;
+    }
+    if (t && t->n - from > 1 && t->s[t->n - 1] == '\r')
+        t->n--;
+}
+
+/* The records of a FASTA or FASTQ file as the reference's reader yields them to gen_ref() (kseq_read, reference
+ * src/kseq.h:184-224, src/genref.c:113): a record starts at the next '>' or '@'; its name ends at the first white
+ * space, the rest of that line is a comment; the sequence is every following line up to one that starts with '>',
+ * '@' or '+' (line feeds and a trailing carriage return dropped, anything else kept, other white space included);
+ * after a '+' line as many quality characters as there were bases are skipped, whatever they are.  A FASTQ record
+ * whose quality is missing or shorter than its sequence ends the file, and is not a record. */
 int sf_fasta_read(const char *path, sf_fasta_t *out, char *err, size_t errcap)
 {
     memset(out, 0, sizeof *out);
-    gzFile fp = gzopen(path, "r");
-    if (!fp) {
+    chars_t in;
+    memset(&in, 0, sizeof in);
+    in.fp = gzopen(path, "r");
+    if (!in.fp) {
         snprintf(err, errcap, "cannot open %s", path);
         return -1;
     }
-    gzbuffer(fp, 1 << 20);
-    size_t cap_b = 1 << 20, n_b = 0;
-    char *bases = (char *)malloc(cap_b);
+    gzbuffer(in.fp, 1 << 20);
+    in.buf = (unsigned char *)malloc(CHARS_BUF);
+    text_t bases = {NULL, 0, 0}, name = {NULL, 0, 0}, qual = {NULL, 0, 0};
     int cap_r = 16, n_r = 0;
     char **names = (char **)malloc(sizeof(char *) * cap_r);
     int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (cap_r + 1));
-    const size_t LINE = 1 << 16;
-    char *line = (char *)malloc(LINE);
-    int in_header = 0; /* a header line longer than the buffer continues */
-    while (gzgets(fp, line, (int)LINE)) {
-        size_t len = strlen(line);
-        const int complete = len && line[len - 1] == '\n';
-        if (in_header) { /* rest of an over-long header: ignore */
-            in_header = !complete;
-            continue;
+    int c, pending = 0; /* pending: the first character of the next header has been taken already */
+    for (;;) {
+        if (!pending) {
+            while ((c = chars_get(&in)) != -1 && c != '>' && c != '@')
+                ;
+            if (c == -1)
+                break;
         }
-        if (line[0] == '>') {
-            if (n_r == cap_r) {
-                cap_r *= 2;
-                names = (char **)realloc(names, sizeof(char *) * cap_r);
-                off = (int64_t *)realloc(off, sizeof(int64_t) * (cap_r + 1));
+        pending = 0;
+        if (chars_at_end(&in))
+            break; /* a header character as the very last byte */
+        name.n = 0;
+        while ((c = chars_get(&in)) != -1 && !isspace(c)) {
+            const unsigned char ch = (unsigned char)c;
+            text_put(&name, &ch, 1);
+        }
+        if (c != -1 && c != '\n')
+            chars_line(&in, NULL, 0); /* comment */
+        const size_t seq0 = bases.n;
+        while ((c = chars_get(&in)) != -1 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n')
+                continue;
+            const unsigned char ch = (unsigned char)c;
+            text_put(&bases, &ch, 1);
+            chars_line(&in, &bases, seq0);
+        }
+        if (c == '>' || c == '@')
+            pending = 1;
+        int bad = 0;
+        if (c == '+') {
+            const size_t n_seq = bases.n - seq0;
+            while ((c = chars_get(&in)) != -1 && c != '\n')
+                ;
+            bad = c == -1;
+            qual.n = 0;
+            while (!bad && !chars_at_end(&in)) {
+                chars_line(&in, &qual, 0);
+                if (qual.n >= n_seq)
+                    break;
             }
-            size_t e = 1;
-            while (line[e] && !isspace((unsigned char)line[e]))
-                e++;
-            names[n_r] = (char *)malloc(e);
-            memcpy(names[n_r], line + 1, e - 1);
-            names[n_r][e - 1] = 0;
-            off[n_r] = (int64_t)n_b;
-            n_r++;
-            in_header = !complete;
-            continue;
+            bad |= qual.n != n_seq;
         }
-        if (n_r == 0)
-            continue; /* text before the first record */
-        if (n_b + len + 1 > cap_b) {
-            while (n_b + len + 1 > cap_b)
-                cap_b *= 2;
-            bases = (char *)realloc(bases, cap_b);
+        if (bad) { /* the reference's loop ends here without this record */
+            bases.n = seq0;
+            break;
         }
-        for (size_t i = 0; i < len; i++)
-            if (!isspace((unsigned char)line[i]))
-                bases[n_b++] = line[i];
+        if (n_r == cap_r) {
+            cap_r *= 2;
+            names = (char **)realloc(names, sizeof(char *) * cap_r);
+            off = (int64_t *)realloc(off, sizeof(int64_t) * (cap_r + 1));
+        }
+        names[n_r] = (char *)malloc(name.n + 1);
+        memcpy(names[n_r], name.s ? name.s : "", name.n);
+        names[n_r][name.n] = 0;
+        off[n_r] = (int64_t)seq0;
+        n_r++;
     }
-    free(line);
-    gzclose(fp);
+    free(in.buf);
+    free(name.s);
+    free(qual.s);
+    gzclose(in.fp);
     if (n_r == 0) {
-        free(bases); free(names); free(off);
+        free(bases.s); free(names); free(off);
         snprintf(err, errcap, "%s holds no FASTA record", path);
         return -1;
     }
-    off[n_r] = (int64_t)n_b;
+    off[n_r] = (int64_t)bases.n;
     out->num_ref = n_r;
     out->names = names;
-    out->bases = bases;
+    out->bases = bases.s ? bases.s : (char *)calloc(1, 1);
     out->off = off;
     return 0;
 }

@@ -243,3 +243,57 @@ def test_patched_reference_over_the_test_double_matches_golden(cli, tmp_path, ca
         assert r.returncode == 0, r.stderr[-2000:]
         want = open(os.path.join(H.GOLDEN, "sam" if sam else "paf", case + (".sam" if sam else ".paf"))).read()
         assert _strip_pg(r.stdout) == _strip_pg(want), (case, sam)  # (without the double there is no device: exit 1)
+
+
+def _fasta_variants(names, seqs, rng):
+    """the same contigs written the ways kseq accepts them (reference src/kseq.h:184-224)"""
+    def wrap(s, w):
+        return [s[i:i + w] for i in range(0, len(s), w)]
+    v = {}
+    v["crlf_comments_blank_lines"] = b"".join(
+        b">" + n.encode() + b" some comment\tmore\r\n" + b"\r\n".join(wrap(s, 61)) + b"\r\n\r\n" for n, s in zip(names, seqs))
+    v["lowercase_and_n"] = b"".join(b">" + n.encode() + b"\n" + b"\n".join(wrap(s[:200].lower() + b"NNNNRY" + s[206:], 70)) + b"\n"
+                                    for n, s in zip(names, seqs))
+    v["text_before_first_record_no_final_newline"] = b"junk line\nmore junk\n" + b"".join(
+        b">" + n.encode() + b"\n" + s + b"\n" for n, s in zip(names, seqs))[:-1]
+    fq = b""
+    for n, s in zip(names, seqs):
+        q = bytes(rng.integers(33, 74, len(s), dtype=np.uint8))
+        q = b"@" + q[1:60] + b">" + q[61:]  # quality lines that start with header characters: skipped by length
+        fq += b"@" + n.encode() + b" desc\n" + b"\n".join(wrap(s, 60)) + b"\n+" + n.encode() + b"\n" + b"\n".join(wrap(q, 60)) + b"\n"
+    v["fastq_multiline"] = fq
+    v["fastq_then_truncated_quality"] = fq + b"@late\nACGTACGTACGTACGT\n+\nIIII\n"  # ends the file, no record
+    v["mixed_fasta_fastq"] = fq[:fq.index(b"@" + names[1].encode())] + b"".join(
+        b">" + n.encode() + b"\n" + s + b"\n" for n, s in zip(names[1:], seqs[1:])) if len(names) > 1 else fq
+    return v
+
+
+@pytest.mark.refbin
+def test_host_reads_fasta_and_fastq_like_the_reference(cli, tmp_path):
+    """the reference file as kseq would read it: Windows line ends, comments, blank lines, lower case and non-ACGT
+    bases, text before the first record, FASTQ (multi-line, quality lines starting with '@' / '>'), a truncated
+    FASTQ record at the end, gzip -- the PAF (contig names, lengths, coordinates) must equal the reference binary's"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(77)
+    k = 6
+    mean, stdv = synth.make_model(k)
+    seqs = [synth.random_sequence(int(n), rng) for n in (2500, 1800, 900)]
+    names = ["chrA", "chrB.1", "c|3"]
+    sigs, _ = synth.simulate_reads(seqs, k, mean, 8, seed=5, bases_per_read=400)
+    ids = [f"r{i}" for i in range(len(sigs))]
+    mf, s5 = str(tmp_path / "model.txt"), str(tmp_path / "reads.blow5")
+    synth.write_model_file(mf, k, mean, stdv)
+    synth.write_blow5(s5, ids, sigs)
+    c = dict(q=250, p=50, flags=0)
+    outs = {}
+    for name, data in _fasta_variants(names, seqs, rng).items():
+        for gz in (False, True):
+            fa = str(tmp_path / (name + (".fa.gz" if gz else ".fa")))
+            with (gzip.open(fa, "wb") if gz else open(fa, "wb")) as f:
+                f.write(data)
+            out, _ = _run(cli, c, fa, s5, mf)
+            assert out == H.run_ref(fa, s5, mf), (name, gz)
+            outs[name] = out
+    assert outs["fastq_multiline"] == outs["fastq_then_truncated_quality"] == outs["crlf_comments_blank_lines"]
+    assert outs["fastq_multiline"].count("\n") == len(ids)
