@@ -78,7 +78,7 @@ static void print_help_msg(FILE *fp, const opt_t *opt)
     fprintf(fp, "Usage: sigfish dtw [OPTIONS] genome.fa reads.blow5\n");
     fprintf(fp, "\nbasic options:\n");
     fprintf(fp, "   -t INT                     number of host threads decoding records [%d]\n", opt->num_thread);
-    fprintf(fp, "   -K INT                     batch size (max number of reads loaded at once) [auto: two GPU waves, >= %d]\n", opt->batch_size);
+    fprintf(fp, "   -K INT                     batch size (max number of reads loaded at once) [auto: ~1e12 DTW cells per GPU, >= %d]\n", opt->batch_size);
     fprintf(fp, "   -B FLOAT[K/M/G]            max number of bytes loaded at once [auto, >= %.1fM]\n", opt->batch_size_bytes / (float)(1000 * 1000));
     fprintf(fp, "   -h                         help\n");
     fprintf(fp, "   -o FILE                    output to file [stdout]\n");
