@@ -25,7 +25,9 @@ def test_shard_range_is_a_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_host_shard_ranges_equal_samples():
+def test_host_shard_ranges_equal_weight():
+    """sf_shard_ranges: contiguous ranges of about the same total weight (the pipeline passes the estimated device work
+    of every read: q x reference columns + 640 cell-times per sample)"""
     B.build_all()
     L = C.CDLL(B.LIB_HOST)
     L.sf_shard_ranges.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
