@@ -297,3 +297,28 @@ def test_host_reads_fasta_and_fastq_like_the_reference(cli, tmp_path):
             outs[name] = out
     assert outs["fastq_multiline"] == outs["fastq_then_truncated_quality"] == outs["crlf_comments_blank_lines"]
     assert outs["fastq_multiline"].count("\n") == len(ids)
+
+
+@pytest.mark.refbin
+def test_host_option_errors_are_the_reference_binarys(cli, tmp_path):
+    """option checking of `dtw` (reference src/dtw_main.c:140-280): same exit status and the same ERROR lines (the
+    reference appends the source position) as the reference binary run right now"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    import re
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_synth48", "blow5")
+    ansi = re.compile(r"\x1b\[[0-9;]*m")
+
+    def errors(cmd, env=None):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        lines = [ansi.sub("", l) for l in r.stderr.splitlines()]
+        keep = [re.sub(r"\s+At \S+:\d+$", "", l).strip() for l in lines if "::ERROR]" in l or "unrecognized option" in l or
+                "requires an argument" in l or "invalid option" in l]
+        return r.returncode != 0, keep
+
+    for extra in (["--dtw-std"], ["--invert"], ["--full-ref"], ["-p", "-1"], ["--pore", "r11"], ["-q", "-5"], ["-K", "0"],
+                  ["-t", "0"], ["-B", "0"], ["--rna", "-p", "-1", "--from-end"], ["--rna", "-p", "-1", "--invert"],
+                  ["--bogus"], ["-K"], ["--sam", "--dtw-std"]):
+        want = errors([H.REF_BIN, "dtw", fa, reads, "--kmer-model", mf] + extra)
+        got = errors([cli, "dtw", fa, reads, "--kmer-model", mf, "--gpus", "1"] + extra, dict(os.environ, MOCK_GPUS="1"))
+        assert got == want, (extra, got, want)  # (an unrecognised option is reported and ignored by both)
