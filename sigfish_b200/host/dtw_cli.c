@@ -251,6 +251,8 @@ int dtw_main(int argc, char *argv[])
             fp_help = stdout;
         } else if (c == 'p') {
             opt.prefix_size = atoi(optarg);
+            if (opt.prefix_size < 0)
+                SF_INFO("%s", "Autodetect query start.");
         } else if (c == 'q') {
             opt.query_size = atoi(optarg);
             if (opt.query_size < 0)

@@ -160,7 +160,7 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
     if (drna_detect(core->sf)) {
         opt.flag |= SIGFISH_RNA;
         if (sf_verbosity >= 3)
-            fprintf(stderr, "[%s] Detected RNA data. --rna was set automatically.\n", __func__);
+            fprintf(stderr, "[INFO] %s: Detected RNA data. --rna was set automatically.\n", __func__); /* VERBOSE(), src/error.h:36 */
     }
     if (opt.pore == NULL) {
         const int8_t pore = pore_detect(core->sf);
@@ -168,7 +168,7 @@ core_t *init_core(const char *fastafile, char *slow5file, opt_t opt, double real
         if (pore) {
             opt.flag |= SIGFISH_R10;
             if (sf_verbosity >= 3)
-                fprintf(stderr, "[%s] Detected %s data. --pore %s was set automatically.\n", __func__,
+                fprintf(stderr, "[INFO] %s: Detected %s data. --pore %s was set automatically.\n", __func__,
                         pore == OPT_PORE_R10 ? "R10" : "RNA004", pore == OPT_PORE_R10 ? "r10" : "rna004");
         }
     }

@@ -153,6 +153,13 @@ def test_host_threaded_epilogue_on_large_batches(cli, tmp_path):
         assert [ln.split("\t")[0] for ln in a.splitlines() if not ln.startswith("@")] == ids
 
 
+def _stable_stderr(text):
+    import re
+    ansi = re.compile(r"\x1b\[[0-9;]*m")
+    keep = ("total entries", "total bytes", "Detected", "Autodetect query start")
+    return [ansi.sub("", l).strip() for l in text.splitlines() if any(k in l for k in keep)]
+
+
 def _fuzz_seeds():
     """12 seeds in the suite; SF_FUZZ_SEEDS=first:last runs another range (long runs are recorded in DESIGN.md 3)"""
     r = os.environ.get("SF_FUZZ_SEEDS", "")
@@ -210,6 +217,10 @@ def test_host_fuzz_matches_reference_binary(cli, tmp_path, seed):
     extra = ["-K", str(int(rng.integers(1, 6))), "-t", str(int(rng.integers(1, 5)))]
     out, err = _run(cli, c, fa, s5, mf, extra, gpus=gpus)
     assert out == H.run_ref(fa, s5, mf, flags=flags, q=q, p=p), (flags, q, p, gpus, extra)
+    # the lines of stderr that do not hold times: chemistry detection, the summary counters
+    r = subprocess.run([H.REF_BIN, "dtw", fa, s5, "--kmer-model", mf, "-q", str(q), "-p", str(p)] + H.flags_to_cli(flags),
+                       capture_output=True, text=True)
+    assert _stable_stderr(err) == _stable_stderr(r.stderr), (flags, q, p)
     if not flags & H.F_DTW:  # the reference aborts on --dtw-std --sam (sigfish.c:669)
         out, _ = _run(cli, c, fa, s5, mf, extra + ["--sam"], gpus=gpus)
         want = H.run_ref(fa, s5, mf, flags=flags, q=q, p=p, extra=["--sam"])
