@@ -142,3 +142,51 @@ def test_patched_reference_keeps_its_cpu_path_and_fails_loudly_without_a_gpu(tmp
     if capi.lib().sfgpu_device_count() == 0:
         r = subprocess.run([acc, "dtw", fa, s5, "--kmer-model", mf, "--accel=yes"], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.refbin
+def test_eval_fuzz_matches_reference_binary(cli, tmp_path):
+    """random truth / test PAF pairs (secondary rows, shifted and missing mappings, shuffled order) through
+    `sigfish-b200 eval` and the reference's `sigfish eval` run right now, every option: identical reports"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+
+    def rows(reads, contigs, sec_p, miss_p):
+        out = []
+        for r in reads:
+            if rng.random() < miss_p:
+                continue
+            for j in range(1 + int(rng.random() < sec_p) * int(rng.integers(1, 4))):
+                st = int(rng.integers(0, 20000))
+                en = st + int(rng.integers(1, 400))
+                out.append(f"{r}\t{int(rng.integers(1000, 9000))}\t{int(rng.integers(0, 300))}\t{int(rng.integers(300, 2000))}\t"
+                           f"{'+-'[int(rng.integers(0, 2))]}\t{contigs[int(rng.integers(0, len(contigs)))]}\t30000\t{st}\t{en}\t"
+                           f"{int(rng.integers(50, 200))}\t{en - st}\t{int(rng.integers(0, 61))}\ttp:A:{'P' if j == 0 else 'S'}")
+        return out
+
+    t_path, q_path = str(tmp_path / "truth.paf"), str(tmp_path / "test.paf")
+    for it in range(48):
+        reads = [f"read_{i}" for i in range(int(rng.integers(1, 40)))]
+        contigs = [f"chr{i}" for i in range(int(rng.integers(1, 4)))]
+        truth = rows(reads, contigs, 0.3, 0.1)
+        test = []
+        for row in truth:
+            u, f = rng.random(), row.split("\t")
+            if u < 0.5:
+                test.append(row)
+            elif u < 0.8:
+                d = int(rng.integers(-300, 300))
+                f[7] = str(max(0, int(f[7]) + d))
+                f[8] = str(max(int(f[7]) + 1, int(f[8]) + d))
+                test.append("\t".join(f))
+        test += rows(reads, contigs, 0.2, 0.5)
+        if rng.random() < 0.3:
+            test = [test[i] for i in rng.permutation(len(test))]
+        open(t_path, "w").write("".join(l + "\n" for l in truth))
+        open(q_path, "w").write("".join(l + "\n" for l in test))
+        opts = [[], ["--tid-only"], ["--secondary", "no"], ["--secondary", "yes"]][it % 4]
+        want = subprocess.run([H.REF_BIN, "eval"] + opts + [t_path, q_path], capture_output=True, text=True)
+        got = run(cli, "eval", *opts, t_path, q_path)
+        assert (got.returncode != 0) == (want.returncode != 0), (it, opts)
+        assert got.stdout == want.stdout, (it, opts)
