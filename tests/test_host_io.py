@@ -494,3 +494,42 @@ def test_record_heads_agree_with_full_decode(host, tmp_path, fmt):
             assert field == np.asarray(sigs[i], np.int16).tobytes()
     assert host.sf_s5_get_next_view(f, C.byref(view)) == 0
     host.sf_s5_close(f)
+
+
+@pytest.mark.parametrize("path", [os.path.join(H.GOLDEN, "sp1_dna.blow5"), "/root/reference/test/sp1_dna.blow5",
+                                  "/root/reference/test/sequin_rna.blow5"])
+def test_record_heads_of_slow5tools_files(host, path):
+    """files written by slow5tools (the reference's own test data: zlib records with auxiliary fields, svb-zd signals):
+    the head of every record -- read by the table-free prefix decoder -- holds the id, scaling and sample count the
+    full decoder finds, and the signal field it points at decodes to the same samples"""
+    if not os.path.exists(path):
+        pytest.skip("reference mount not present")
+    import struct
+    import zlib
+    full = read_all(host, path)[0]
+    host.sf_zlib_inflate_prefix.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                            C.POINTER(C.c_size_t)]
+    host.sf_zlib_inflate_prefix.restype = C.c_int
+    err = C.create_string_buffer(512)
+    f = host.sf_s5_open(path.encode(), err, 512)
+    assert f and host.sf_s5_record_press(f) == 1 and host.sf_s5_signal_press(f) == 1
+    scratch, scap = C.c_void_p(), C.c_size_t(0)
+    state, out, got = C.create_string_buffer(1 << 16), C.create_string_buffer(512), C.c_size_t(0)
+    answered = 0
+    for want in full:
+        view = C.c_void_p()
+        n = host.sf_s5_get_next_view(f, C.byref(view))
+        assert n > 0
+        rec, pos, nbytes = SfRec(), C.c_int32(), C.c_int64()
+        assert host.sf_s5_parse_head(f, view, n, C.byref(rec), C.byref(pos), C.byref(nbytes), C.byref(scratch), C.byref(scap)) == 0
+        assert (rec.read_id.decode(), rec.digitisation, rec.offset, rec.range, rec.sampling_rate) == want[:5]
+        assert rec.len_raw_signal == len(want[5])
+        raw = C.string_at(view, n)
+        body = zlib.decompress(raw)
+        field = body[pos.value:pos.value + nbytes.value]
+        assert struct.unpack("<I", field[:4])[0] == len(want[5])
+        assert field == synth._svb_zd_encode(want[5])
+        answered += host.sf_zlib_inflate_prefix(state, raw, len(raw), out, 384, 48, C.byref(got))
+        assert out.raw[:got.value] == body[:got.value]
+    assert answered == len(full)  # these streams start with a dynamic block that holds the whole head
+    host.sf_s5_close(f)
