@@ -190,3 +190,21 @@ def test_eval_fuzz_matches_reference_binary(cli, tmp_path):
         got = run(cli, "eval", *opts, t_path, q_path)
         assert (got.returncode != 0) == (want.returncode != 0), (it, opts)
         assert got.stdout == want.stdout, (it, opts)
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("truth,test", [("sp1_dna.minimap2.paf", "dna_sp1_default.paf"),
+                                        ("sequin_rna.minimap2.paf", "rna_sequin_q500_auto.paf")])
+def test_eval_on_the_reference_truth_sets(cli, truth, test):
+    """the EVALUATE step of the reference's test/test.sh:23-42: its minimap2 truth sets against the mappings of its two
+    test commands (golden PAF; made with a synthetic pore model, so `correct` is low -- the comparison is between the
+    two eval implementations, not against the script's thresholds, which need the built-in pore tables)"""
+    t = os.path.join("/root/reference/test", truth)
+    if not (H.have_ref_bin() and os.path.exists(t)):
+        pytest.skip("reference mount / oracle/_ref not present")
+    q = os.path.join(H.GOLDEN, "paf", test)
+    for opts in ([], ["--tid-only"], ["--secondary", "no"]):
+        want = subprocess.run([H.REF_BIN, "eval"] + opts + [t, q], capture_output=True, text=True)
+        got = run(cli, "eval", *opts, t, q)
+        assert want.returncode == 0 and got.returncode == 0
+        assert got.stdout == want.stdout and "mapped_testset" in got.stdout
