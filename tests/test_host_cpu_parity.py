@@ -333,3 +333,34 @@ def test_host_option_errors_are_the_reference_binarys(cli, tmp_path):
         want = errors([H.REF_BIN, "dtw", fa, reads, "--kmer-model", mf] + extra)
         got = errors([cli, "dtw", fa, reads, "--kmer-model", mf, "--gpus", "1"] + extra, dict(os.environ, MOCK_GPUS="1"))
         assert got == want, (extra, got, want)  # (an unrecognised option is reported and ignored by both)
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("reads,fasta,k,args", [
+    ("sp1_dna", "nCoV-2019", 6, []),
+    ("sp1_dna", "nCoV-2019", 6, ["--from-end"]),
+    ("sequin_rna", "rnasequin", 5, ["--rna", "-q", "500", "-p", "-1"]),
+    ("sequin_rna", "rnasequin", 5, ["--rna", "--full-ref", "-q", "500", "-p", "-1"]),
+    ("sequin_rna", "rnasequin", 5, ["--rna", "--from-end", "-q", "500"]),
+    ("sequin_rna", "rnasequin", 5, ["--rna", "--full-ref", "--from-end", "-q", "500"]),
+])
+def test_host_runs_the_reference_test_script_commands(cli, tmp_path, reads, fasta, k, args):
+    """the six `sigfish dtw` commands of the reference's test/test.sh and test/test_extensive.sh (lines 58-86) on its
+    own reads and references (synthetic pore model: the built-in tables are absent from the mount), both binaries
+    run right now with the script's -t 8: the PAF must be identical"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    ids, sigs, sc = H.load_reads_npz(os.path.join(H.GOLDEN, reads + ".npz"))
+    s5, fa, mf = str(tmp_path / "reads.blow5"), str(tmp_path / "ref.fa"), str(tmp_path / "model.txt")
+    synth.write_blow5(s5, ids, sigs, rna="--rna" in args, scalings=sc)
+    with gzip.open(os.path.join(H.GOLDEN, fasta + ".fa.gz"), "rb") as fi, open(fa, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    mean, stdv = synth.make_model(k)
+    synth.write_model_file(mf, k, mean, stdv)
+    want = subprocess.run([H.REF_BIN, "dtw", fa, s5, "--kmer-model", mf, "-t", "8"] + args, capture_output=True, text=True)
+    assert want.returncode == 0, want.stderr[-2000:]
+    got = subprocess.run([cli, "dtw", fa, s5, "--kmer-model", mf, "-t", "8", "--gpus", "2"] + args, capture_output=True, text=True,
+                         env=dict(os.environ, MOCK_GPUS="2"))
+    assert got.returncode == 0, got.stderr[-2000:]
+    assert got.stdout == want.stdout and got.stdout.count("\n") == len(ids)
+    assert _stable_stderr(got.stderr) == _stable_stderr(want.stderr)
