@@ -364,3 +364,30 @@ def test_host_runs_the_reference_test_script_commands(cli, tmp_path, reads, fast
     assert got.returncode == 0, got.stderr[-2000:]
     assert got.stdout == want.stdout and got.stdout.count("\n") == len(ids)
     assert _stable_stderr(got.stderr) == _stable_stderr(want.stderr)
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("fasta,blow5,k,args", [
+    ("nCoV-2019.reference.fasta", "sp1_dna.blow5", 6, []),
+    ("rnasequin_sequences_2.4.fa", "sequin_rna.blow5", 5, ["--rna", "-q", "500", "-p", "-1"]),
+])
+def test_host_on_the_reference_files_as_they_are(cli, tmp_path, fasta, blow5, k, args):
+    """test/test.sh's two commands on the reference's files themselves (slow5tools-written BLOW5 with auxiliary fields,
+    its FASTA files), records path and host-decode path"""
+    d = "/root/reference/test"
+    if not (H.have_ref_bin() and os.path.exists(os.path.join(d, blow5))):
+        pytest.skip("reference mount / oracle/_ref not present")
+    mf = str(tmp_path / "model.txt")
+    mean, stdv = synth.make_model(k)
+    synth.write_model_file(mf, k, mean, stdv)
+    base = ["dtw", os.path.join(d, fasta), os.path.join(d, blow5), "--kmer-model", mf, "-t", "8"] + args
+    want = subprocess.run([H.REF_BIN] + base, capture_output=True, text=True)
+    assert want.returncode == 0 and want.stdout.count("\n") >= 5
+    for extra in ([], ["--device-decode=no"], ["--sam"]):
+        got = subprocess.run([cli] + base + ["--gpus", "2"] + extra, capture_output=True, text=True, env=dict(os.environ, MOCK_GPUS="2"))
+        assert got.returncode == 0, got.stderr[-2000:]
+        if "--sam" in extra:
+            ref_sam = subprocess.run([H.REF_BIN] + base + ["--sam"], capture_output=True, text=True)
+            assert _strip_pg(got.stdout) == _strip_pg(ref_sam.stdout)
+        else:
+            assert got.stdout == want.stdout
