@@ -391,3 +391,24 @@ def test_host_on_the_reference_files_as_they_are(cli, tmp_path, fasta, blow5, k,
             assert _strip_pg(got.stdout) == _strip_pg(ref_sam.stdout)
         else:
             assert got.stdout == want.stdout
+
+
+@pytest.mark.refbin
+def test_host_misc_options_behave_like_the_reference(cli, tmp_path):
+    """options that do not change the mapping (or only where it goes): same exit status, same stdout, same -o file"""
+    if not H.have_ref_bin():
+        pytest.skip("oracle/_ref not built")
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_synth48", "blow5")
+    out_r, out_h = str(tmp_path / "r.paf"), str(tmp_path / "h.paf")
+    for extra in (["--accel=yes"], ["--accel=no"], ["--profile-cpu=yes"], ["--profile-cpu=maybe"], ["--verbose", "0"],
+                  ["--verbose", "6"], ["-o", "FILE"], ["-o", "-"], ["--secondary=yes"], ["-a"], ["-w", "chr1:1-100"],
+                  ["--kmer-model", "nofile.txt"], ["-K", "5", "--debug-break=yes"]):
+        ex_r = [out_r if x == "FILE" else x for x in extra]
+        ex_h = [out_h if x == "FILE" else x for x in extra]
+        want = subprocess.run([H.REF_BIN, "dtw", fa, reads, "--kmer-model", mf] + ex_r, capture_output=True, text=True)
+        got = subprocess.run([cli, "dtw", fa, reads, "--kmer-model", mf, "--gpus", "1"] + ex_h, capture_output=True, text=True,
+                             env=dict(os.environ, MOCK_GPUS="1"))
+        assert got.returncode == want.returncode, extra
+        assert _strip_pg(got.stdout) == _strip_pg(want.stdout), extra
+        if "FILE" in extra:
+            assert open(out_h).read() == open(out_r).read() and got.stdout == ""
