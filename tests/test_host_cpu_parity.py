@@ -398,11 +398,11 @@ def test_host_misc_options_behave_like_the_reference(cli, tmp_path):
     """options that do not change the mapping (or only where it goes): same exit status, same stdout, same -o file"""
     if not H.have_ref_bin():
         pytest.skip("oracle/_ref not built")
-    c, fa, reads, mf = _inputs(str(tmp_path), "dna_synth48", "blow5")
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "blow5")
     out_r, out_h = str(tmp_path / "r.paf"), str(tmp_path / "h.paf")
     for extra in (["--accel=yes"], ["--accel=no"], ["--profile-cpu=yes"], ["--profile-cpu=maybe"], ["--verbose", "0"],
                   ["--verbose", "6"], ["-o", "FILE"], ["-o", "-"], ["--secondary=yes"], ["-a"], ["-w", "chr1:1-100"],
-                  ["--kmer-model", "nofile.txt"], ["-K", "5", "--debug-break=yes"]):
+                  ["--kmer-model", "nofile.txt"], ["-K", "2", "--debug-break=yes"]):
         ex_r = [out_r if x == "FILE" else x for x in extra]
         ex_h = [out_h if x == "FILE" else x for x in extra]
         want = subprocess.run([H.REF_BIN, "dtw", fa, reads, "--kmer-model", mf] + ex_r, capture_output=True, text=True)
