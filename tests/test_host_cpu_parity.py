@@ -136,8 +136,8 @@ def test_host_threaded_epilogue_on_large_batches(cli, tmp_path):
     """batches of >= 1024 reads run the epilogue on the -t threads in chunks of 512 reads: same bytes as small batches"""
     k = 6
     mean, stdv = synth.make_model(k)
-    seq = synth.random_sequence(1500, np.random.default_rng(9))
-    base, _ = synth.simulate_reads([seq], k, mean, 40, seed=12, bases_per_read=300)
+    seq = synth.random_sequence(900, np.random.default_rng(9))
+    base, _ = synth.simulate_reads([seq], k, mean, 40, seed=12, bases_per_read=220)
     n = 2300
     sigs = [base[i % len(base)] for i in range(n)]
     ids = [f"read_{i:06d}" for i in range(n)]
@@ -145,7 +145,7 @@ def test_host_threaded_epilogue_on_large_batches(cli, tmp_path):
     synth.write_fasta(fa, ["chrT"], [seq])
     synth.write_model_file(mf, k, mean, stdv)
     synth.write_blow5(b5, ids, sigs)
-    c = dict(q=100, p=50, flags=0)
+    c = dict(q=50, p=20, flags=0)
     for extra in ([], ["--sam"]):
         a, _ = _run(cli, c, fa, b5, mf, ["-t", "8", "-K", "4096", "-B", "100G"] + extra, gpus=2)
         b, _ = _run(cli, c, fa, b5, mf, ["-t", "2", "-K", "200", "-B", "100G"] + extra)
