@@ -93,6 +93,11 @@ int sfgpu_set_ref(sfgpu_ctx *c, int32_t num_ref, const char *bases, const int64_
     for (int32_t i = 0; i < num_ref; i++) {
         seqs[i] = bases + base_off[i];
         lens[i] = (int32_t)(base_off[i + 1] - base_off[i]);
+        if (base_off[i + 1] - base_off[i] < c->opt.kmer_size) { /* as libsfgpu.so does (sfgpu.cu: sfgpu_set_ref) */
+            free(seqs);
+            free(lens);
+            return fail(c, SFGPU_EARG, "a contig is shorter than the k-mer size");
+        }
     }
     if (c->ref)
         orc_ref_free(c->ref);

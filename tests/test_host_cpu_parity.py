@@ -412,3 +412,15 @@ def test_host_misc_options_behave_like_the_reference(cli, tmp_path):
         assert _strip_pg(got.stdout) == _strip_pg(want.stdout), extra
         if "FILE" in extra:
             assert open(out_h).read() == open(out_r).read() and got.stdout == ""
+
+
+def test_host_refuses_contigs_shorter_than_k(cli, tmp_path):
+    """a contig with fewer bases than the k-mer size: the reference binary dies with a segmentation fault (gen_ref
+    computes a negative length); the library refuses it (SFGPU_EARG) and the command line says so and exits 1"""
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "blow5")
+    for head in (b">empty\n", b">tiny\nACG\n"):
+        bad = str(tmp_path / "bad.fa")
+        open(bad, "wb").write(head + open(fa, "rb").read())
+        r = subprocess.run([cli, "dtw", bad, reads, "--kmer-model", mf, "--gpus", "1"], capture_output=True, text=True,
+                           env=dict(os.environ, MOCK_GPUS="1"))
+        assert r.returncode == 1 and "ERROR" in r.stderr and r.stdout == ""
