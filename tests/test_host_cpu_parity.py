@@ -424,3 +424,20 @@ def test_host_refuses_contigs_shorter_than_k(cli, tmp_path):
         r = subprocess.run([cli, "dtw", bad, reads, "--kmer-model", mf, "--gpus", "1"], capture_output=True, text=True,
                            env=dict(os.environ, MOCK_GPUS="1"))
         assert r.returncode == 1 and "ERROR" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.parametrize("fmt,extra", [("blow5", []), ("blow5", ["--device-decode=no"]), ("slow5", [])])
+def test_host_empty_reads_print_nothing(cli, tmp_path, fmt, extra):
+    """reads without samples (reference src/sigfish.c:1068-1070: nothing is printed for them; its binary crashes on
+    some such files) between ordinary reads: the other rows are what they are without the empty reads"""
+    c, fa, reads, mf = _inputs(str(tmp_path), "dna_sp1_default", "blow5")
+    ids, sigs, sc = H.case_reads(CASES["dna_sp1_default"])
+    ids2 = ["e0"] + list(ids[:2]) + ["e1"] + list(ids[2:]) + ["e2"]
+    z = np.zeros(0, dtype=np.int16)
+    sigs2 = [z] + list(sigs[:2]) + [z] + list(sigs[2:]) + [z]
+    sc2 = [sc[0]] + list(sc[:2]) + [sc[0]] + list(sc[2:]) + [sc[0]]
+    p = str(tmp_path / ("with_empty." + fmt))
+    (synth.write_blow5 if fmt == "blow5" else synth.write_slow5_ascii)(p, ids2, sigs2, scalings=sc2)
+    out, err = _run(cli, c, fa, p, mf, extra + ["-K", "3"], gpus=2)
+    assert out == open(os.path.join(H.GOLDEN, "paf", "dna_sp1_default.paf")).read()
+    assert f"total entries: {len(ids2)}" in err
